@@ -1,0 +1,473 @@
+// Attention kernels of the GPT-NeoX path: the per-token decode attention over the KV cache (HBM-bound) and the
+// prefill-side bias + rotary + cache scatter and causal attention.
+//
+// Reference behaviour restated (not ported):
+//   * decode: masked_multihead_attention_kernel,
+//     kernels/decoder_masked_multihead_attention/decoder_masked_multihead_attention_template.hpp:1099-1919 --
+//     q,k,v += bias (fp16), NeoX rotary on the first `rot` dims pairing (i, i + rot/2) at position
+//     timestep - pad_count (:1303-1365, utils.h:1325-1337), append k,v at slot seq_len[b], scores = q.k / sqrt(dh) in
+//     fp32, the pad gap [input_len, max_input_len) is masked, softmax with 1/(sum + 1e-6), out = P.V;
+//     finished rows return immediately (:1176-1178).
+//   * prefill: add_fusedQKV_bias_transpose_kernel + transpose_4d_batch_major_{k,v}_cache
+//     (kernels/unfused_attention_kernels.cu:1326-1484,1673-1757) and the unfused QK^T / masked softmax / PV chain
+//     (layers/attention_layers/GptContextAttentionLayer.cc:194-300, unfused_attention_kernels.cu:255-333).
+//
+// B200 design of the decode kernel (roofline: HBM, 2 * c * dh * 2 bytes per (sequence, head) per step):
+//   * cache layout K,V = [B, heads, max_len, dh] fp16: one (b, h) pair is a single contiguous stream;
+//   * a cache row (dh halves) is read by dh/8 adjacent lanes with one 128-bit no-allocate load each, four rows in
+//     flight per lane; dot products reduced with warp shuffles inside the row group;
+//   * split-KV: grid = (heads, B, splits) so that B*heads*splits covers the 148 SMs several times even at B = 1;
+//     every split writes (max, sum, unnormalised out) and the last CTA to arrive (atomic ticket, self-resetting)
+//     merges them -- no second launch;
+//   * masked pad-gap rows are never loaded.
+#include "common.cuh"
+
+namespace ftcf {
+
+constexpr int MMHA_THREADS = 128;
+constexpr int MMHA_MAX_CHUNK = 4096;   // keys per split (fp32 scores kept in shared memory)
+
+__device__ __forceinline__ float rotary_angle(int pos, int i, int rot)
+{
+    // decoder_masked_multihead_attention_utils.h:1325-1329: t_step / 10000^(2i/rot)
+    return (float)pos / powf(10000.f, (2.f * (float)i) / (float)rot);
+}
+
+// x[d] (already biased, fp16) and its NeoX partner -> rotated value, rounded to fp16
+__device__ __forceinline__ __half rotary_neox(__half xd, __half xpartner, int d, int rot, int pos)
+{
+    const int half_rot = rot >> 1;
+    const int i = d < half_rot ? d : d - half_rot;
+    float sn, cs;
+    sincosf(rotary_angle(pos, i, rot), &sn, &cs);
+    const float a = __half2float(xd), b = __half2float(xpartner);
+    return __float2half_rn(d < half_rot ? cs * a - sn * b : cs * a + sn * b);
+}
+
+struct MmhaP {
+    ftcf_mmha_params p;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP params)
+{
+    const ftcf_mmha_params& p = params.p;
+    constexpr int LPR = DH / 8;               // lanes per cache row (16 bytes each)
+    constexpr int NG = MMHA_THREADS / LPR;    // row groups per CTA
+    constexpr int UNR = 4;
+
+    __shared__ float s_scores[MMHA_MAX_CHUNK];
+    __shared__ float s_out[NG][DH];
+    __shared__ __align__(16) __half s_q[DH];
+    __shared__ __align__(16) __half s_k[DH];
+    __shared__ __align__(16) __half s_v[DH];
+    __shared__ float s_red[32];
+    __shared__ int s_flag;
+
+    const int h = blockIdx.x, b = blockIdx.y, split = blockIdx.z;
+    const int H = p.heads, tid = threadIdx.x;
+    if (p.finished != nullptr && p.finished[b]) return;
+
+    const int tlen = p.seq_len[b];
+    const int total = tlen + 1;
+    const int chunk = ceil_div(total, p.splits);
+    const int start = split * chunk;
+    const int end = min(start + chunk, total);
+    const int owner = tlen / chunk;           // the split that holds the new token
+    const int in_len = p.input_len[b], max_in = p.max_input_len;
+
+    const __half* qkv = static_cast<const __half*>(p.qkv) + (size_t)b * 3 * H * DH;
+    const __half* bias = static_cast<const __half*>(p.qkv_bias);
+    __half* kc = static_cast<__half*>(p.k_cache) + ((size_t)b * H + h) * (size_t)p.max_len * DH;
+    __half* vc = static_cast<__half*>(p.v_cache) + ((size_t)b * H + h) * (size_t)p.max_len * DH;
+
+    // ---- q (all splits), k / v (owner split): bias, rotary, append to the cache
+    for (int d = tid; d < DH; d += MMHA_THREADS) {
+        const int rot = p.rotary_dim;
+        const int pos = (*p.step - 1) - p.pad_count[b];
+        const int qi = h * DH + d;
+        __half q = qkv[qi];
+        if (bias) q = __hadd(q, bias[qi]);
+        const bool do_rot = d < rot;
+        const int dp = d < (rot >> 1) ? d + (rot >> 1) : d - (rot >> 1);
+        if (do_rot) {
+            __half qp = qkv[h * DH + dp];
+            if (bias) qp = __hadd(qp, bias[h * DH + dp]);
+            q = rotary_neox(q, qp, d, rot, pos);
+        }
+        s_q[d] = q;
+        if (split == owner) {
+            const int ki = H * DH + qi, vi = 2 * H * DH + qi;
+            __half k = qkv[ki], v = qkv[vi];
+            if (bias) {
+                k = __hadd(k, bias[ki]);
+                v = __hadd(v, bias[vi]);
+            }
+            if (do_rot) {
+                __half kp = qkv[H * DH + h * DH + dp];
+                if (bias) kp = __hadd(kp, bias[H * DH + h * DH + dp]);
+                k = rotary_neox(k, kp, d, rot, pos);
+            }
+            s_k[d] = k;
+            s_v[d] = v;
+            kc[(size_t)tlen * DH + d] = k;
+            vc[(size_t)tlen * DH + d] = v;
+        }
+    }
+    __syncthreads();
+
+    const int li = tid % LPR, gi = tid / LPR;
+    float q[8];
+    {
+        const uint4 qv = *reinterpret_cast<const uint4*>(&s_q[li * 8]);
+        const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(qh[i]);
+            q[2 * i] = f.x;
+            q[2 * i + 1] = f.y;
+        }
+    }
+
+    // ---- scores
+    for (int base = start; base < end; base += NG * UNR) {
+        uint4 kv[UNR];
+        bool valid[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int pos = base + gi + u * NG;
+            valid[u] = pos < end && !(pos >= in_len && pos < max_in);
+            kv[u] = make_uint4(0, 0, 0, 0);
+            if (valid[u]) {
+                if (pos == tlen) kv[u] = *reinterpret_cast<const uint4*>(&s_k[li * 8]);
+                else kv[u] = ld_stream_16(kc + (size_t)pos * DH + li * 8);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const __half2* kh = reinterpret_cast<const __half2*>(&kv[u]);
+            float dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(kh[i]);
+                dot = fmaf(q[2 * i], f.x, dot);
+                dot = fmaf(q[2 * i + 1], f.y, dot);
+            }
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            const int pos = base + gi + u * NG;
+            if (li == 0 && pos < end) s_scores[pos - start] = valid[u] ? dot * p.inv_sqrt_dh : -INFINITY;
+        }
+    }
+    __syncthreads();
+
+    // ---- softmax statistics of this split
+    const int cnt = max(end - start, 0);
+    float mx = -INFINITY;
+    for (int i = tid; i < cnt; i += MMHA_THREADS) mx = fmaxf(mx, s_scores[i]);
+    mx = block_max(mx, s_red);
+    float sum = 0.f;
+    for (int i = tid; i < cnt; i += MMHA_THREADS) {
+        const float sc = s_scores[i];
+        const float e = (sc == -INFINITY) ? 0.f : __expf(sc - mx);
+        s_scores[i] = e;
+        sum += e;
+    }
+    sum = block_sum(sum, s_red);
+    __syncthreads();
+
+    // ---- P.V
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int base = start; base < end; base += NG * UNR) {
+        uint4 vv[UNR];
+        float pr[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int pos = base + gi + u * NG;
+            pr[u] = pos < end ? s_scores[pos - start] : 0.f;
+            vv[u] = make_uint4(0, 0, 0, 0);
+            if (pr[u] != 0.f) {
+                if (pos == tlen) vv[u] = *reinterpret_cast<const uint4*>(&s_v[li * 8]);
+                else vv[u] = ld_stream_16(vc + (size_t)pos * DH + li * 8);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const __half2* vh = reinterpret_cast<const __half2*>(&vv[u]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(vh[i]);
+                acc[2 * i] = fmaf(pr[u], f.x, acc[2 * i]);
+                acc[2 * i + 1] = fmaf(pr[u], f.y, acc[2 * i + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_out[gi][li * 8 + i] = acc[i];
+    __syncthreads();
+
+    __half* ctx = static_cast<__half*>(p.ctx) + (size_t)b * H * DH + h * DH;
+    if (p.splits == 1) {
+        for (int d = tid; d < DH; d += MMHA_THREADS) {
+            float o = 0.f;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) o += s_out[g][d];
+            ctx[d] = __float2half_rn(o * (1.f / (sum + 1e-6f)));
+        }
+        return;
+    }
+
+    // ---- split-KV: publish the partial, the last arriver merges
+    float* part = p.partial + ((size_t)(b * H + h) * p.splits + split) * (DH + 2);
+    for (int d = tid; d < DH; d += MMHA_THREADS) {
+        float o = 0.f;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) o += s_out[g][d];
+        part[d] = o;
+    }
+    if (tid == 0) {
+        part[DH] = mx;
+        part[DH + 1] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int old = atomicAdd(&p.counters[b * H + h], 1);
+        s_flag = (old == p.splits - 1);
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    __threadfence();
+    const float* all = p.partial + (size_t)(b * H + h) * p.splits * (DH + 2);
+    float M = -INFINITY;
+    for (int s2 = 0; s2 < p.splits; ++s2) M = fmaxf(M, __ldcg(&all[s2 * (DH + 2) + DH]));
+    for (int d = tid; d < DH; d += MMHA_THREADS) {
+        float L = 0.f, O = 0.f;
+        for (int s2 = 0; s2 < p.splits; ++s2) {
+            const float mi = __ldcg(&all[s2 * (DH + 2) + DH]);
+            const float wgt = (mi == -INFINITY) ? 0.f : __expf(mi - M);
+            L = fmaf(__ldcg(&all[s2 * (DH + 2) + DH + 1]), wgt, L);
+            O = fmaf(__ldcg(&all[s2 * (DH + 2) + d]), wgt, O);
+        }
+        ctx[d] = __float2half_rn(O * (1.f / (L + 1e-6f)));
+    }
+    if (tid == 0) p.counters[b * H + h] = 0;
+}
+
+// ---------------------------------------------------------------- prefill: bias + rotary + scatter
+template <int DH>
+__global__ void __launch_bounds__(DH)
+prefill_qkv_rotary_scatter_kernel(const __half* __restrict__ qkv, const __half* __restrict__ bias, __half* __restrict__ q_out,
+                                  __half* __restrict__ k_cache, __half* __restrict__ v_cache,
+                                  const int32_t* __restrict__ tok_batch, const int32_t* __restrict__ tok_pos, int H, int rot,
+                                  int max_len)
+{
+    const int tkn = blockIdx.x, h = blockIdx.y, d = threadIdx.x;
+    const int b = tok_batch[tkn], pos = tok_pos[tkn];
+    const __half* row = qkv + (size_t)tkn * 3 * H * DH;
+    const int qi = h * DH + d, ki = H * DH + qi, vi = 2 * H * DH + qi;
+    __half q = row[qi], k = row[ki], v = row[vi];
+    if (bias) {
+        q = __hadd(q, bias[qi]);
+        k = __hadd(k, bias[ki]);
+        v = __hadd(v, bias[vi]);
+    }
+    if (d < rot) {
+        const int dp = d < (rot >> 1) ? d + (rot >> 1) : d - (rot >> 1);
+        __half qp = row[h * DH + dp], kp = row[H * DH + h * DH + dp];
+        if (bias) {
+            qp = __hadd(qp, bias[h * DH + dp]);
+            kp = __hadd(kp, bias[H * DH + h * DH + dp]);
+        }
+        q = rotary_neox(q, qp, d, rot, pos);
+        k = rotary_neox(k, kp, d, rot, pos);
+    }
+    q_out[((size_t)tkn * H + h) * DH + d] = q;
+    const size_t ci = (((size_t)b * H + h) * max_len + pos) * DH + d;
+    k_cache[ci] = k;
+    v_cache[ci] = v;
+}
+
+// ---------------------------------------------------------------- prefill: causal attention (CUDA-core flash form)
+// 4 lanes per query row, 32 query rows per CTA, K/V tiles of 32 keys staged in shared memory, online softmax.
+template <int DH>
+__global__ void __launch_bounds__(128)
+prefill_attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k_cache, const __half* __restrict__ v_cache,
+                         __half* __restrict__ ctx, const int32_t* __restrict__ seq_offsets, int H, int max_len, float scale)
+{
+    constexpr int QT = 32, KT = 32, DPL = DH / 4, NV = DPL / 8;   // dims per lane, 16-byte vectors per lane
+    __shared__ __align__(16) __half s_k[KT][DH];
+    __shared__ __align__(16) __half s_v[KT][DH];
+
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
+    const int off = seq_offsets[b], len = seq_offsets[b + 1] - off;
+    if (q0 >= len) return;
+    const int tid = threadIdx.x, li = tid & 3, qi = q0 + (tid >> 2);
+    const bool q_ok = qi < len;
+
+    float qr[DPL], o[DPL];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (q_ok) v = *reinterpret_cast<const uint4*>(q + ((size_t)(off + qi) * H + h) * DH + c * 32 + li * 8);
+        const __half2* vh = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(vh[i]);
+            qr[c * 8 + 2 * i] = f.x;
+            qr[c * 8 + 2 * i + 1] = f.y;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) o[i] = 0.f;
+    float mrun = -INFINITY, lrun = 0.f;
+
+    const __half* kb = k_cache + ((size_t)b * H + h) * (size_t)max_len * DH;
+    const __half* vb = v_cache + ((size_t)b * H + h) * (size_t)max_len * DH;
+    const int kmax = min(q0 + QT, len);   // keys needed by this CTA: [0, kmax)
+    for (int k0 = 0; k0 < kmax; k0 += KT) {
+        __syncthreads();
+        for (int v = tid; v < KT * DH / 8; v += 128) {
+            const int r = v / (DH / 8), c = v % (DH / 8);
+            uint4 kk = make_uint4(0, 0, 0, 0), vv = kk;
+            if (k0 + r < kmax) {
+                kk = *reinterpret_cast<const uint4*>(kb + (size_t)(k0 + r) * DH + c * 8);
+                vv = *reinterpret_cast<const uint4*>(vb + (size_t)(k0 + r) * DH + c * 8);
+            }
+            *reinterpret_cast<uint4*>(&s_k[r][c * 8]) = kk;
+            *reinterpret_cast<uint4*>(&s_v[r][c * 8]) = vv;
+        }
+        __syncthreads();
+        const int jend = min(KT, kmax - k0);
+        for (int j = 0; j < jend; ++j) {
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                const uint4 kk = *reinterpret_cast<const uint4*>(&s_k[j][c * 32 + li * 8]);
+                const __half2* kh = reinterpret_cast<const __half2*>(&kk);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(kh[i]);
+                    dot = fmaf(qr[c * 8 + 2 * i], f.x, dot);
+                    dot = fmaf(qr[c * 8 + 2 * i + 1], f.y, dot);
+                }
+            }
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            if (k0 + j <= qi) {                       // causal (uniform inside the 4-lane group)
+                const float sc = dot * scale;
+                if (sc > mrun) {
+                    const float corr = __expf(mrun - sc);   // exp(-inf) = 0 on the first key
+                    lrun *= corr;
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) o[i] *= corr;
+                    mrun = sc;
+                }
+                const float pr = __expf(sc - mrun);
+                lrun += pr;
+#pragma unroll
+                for (int c = 0; c < NV; ++c) {
+                    const uint4 vv = *reinterpret_cast<const uint4*>(&s_v[j][c * 32 + li * 8]);
+                    const __half2* vh = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = __half22float2(vh[i]);
+                        o[c * 8 + 2 * i] = fmaf(pr, f.x, o[c * 8 + 2 * i]);
+                        o[c * 8 + 2 * i + 1] = fmaf(pr, f.y, o[c * 8 + 2 * i + 1]);
+                    }
+                }
+            }
+        }
+    }
+    if (!q_ok) return;
+    const float inv = 1.f / lrun;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+        uint4 out;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&out);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ow[i] = f2_to_h2(o[c * 8 + 2 * i] * inv, o[c * 8 + 2 * i + 1] * inv);
+        *reinterpret_cast<uint4*>(ctx + (size_t)(off + qi) * H * DH + h * DH + c * 32 + li * 8) = out;
+    }
+}
+
+}  // namespace ftcf
+
+using namespace ftcf;
+
+extern "C" int ftcf_mmha_choose_splits(int batch, int heads, int max_len)
+{
+    const int ctas = batch * heads;
+    int splits = ceil_div(148 * 4, ctas > 0 ? ctas : 1);
+    const int by_len = ceil_div(max_len, 128);          // at least 128 keys per split
+    if (splits > by_len) splits = by_len;
+    const int need = ceil_div(max_len, MMHA_MAX_CHUNK); // at most MMHA_MAX_CHUNK keys per split
+    if (splits < need) splits = need;
+    if (splits < 1) splits = 1;
+    return splits;
+}
+
+extern "C" int ftcf_mmha_decode(const ftcf_mmha_params* p, void* stream)
+{
+    FTCF_REQUIRE(p != nullptr, FTCF_ERR_INVALID, "mmha: null params");
+    FTCF_REQUIRE(p->batch > 0 && p->heads > 0 && p->splits >= 1, FTCF_ERR_INVALID, "mmha: bad sizes");
+    FTCF_REQUIRE(ceil_div(p->max_len, p->splits) <= MMHA_MAX_CHUNK, FTCF_ERR_INVALID,
+                 "mmha: max_len %d needs at least %d splits", p->max_len, ceil_div(p->max_len, MMHA_MAX_CHUNK));
+    FTCF_REQUIRE(p->splits == 1 || (p->partial != nullptr && p->counters != nullptr), FTCF_ERR_INVALID,
+                 "mmha: split-KV needs scratch");
+    FTCF_REQUIRE(p->rotary_dim % 2 == 0 && p->rotary_dim <= p->dh, FTCF_ERR_INVALID, "mmha: rotary_dim %d", p->rotary_dim);
+    MmhaP mp{*p};
+    const dim3 grid(p->heads, p->batch, p->splits);
+    switch (p->dh) {
+        case 64: mmha_decode_kernel<64><<<grid, MMHA_THREADS, 0, as_stream(stream)>>>(mp); break;
+        case 128: mmha_decode_kernel<128><<<grid, MMHA_THREADS, 0, as_stream(stream)>>>(mp); break;
+        case 256: mmha_decode_kernel<256><<<grid, MMHA_THREADS, 0, as_stream(stream)>>>(mp); break;
+        default: FTCF_REQUIRE(false, FTCF_ERR_UNSUPPORTED, "mmha: size_per_head %d (supported: 64, 128, 256)", p->dh);
+    }
+    FTCF_LAUNCH_CHECK();
+    return FTCF_OK;
+}
+
+extern "C" int ftcf_prefill_qkv_rotary_scatter(const void* qkv, const void* qkv_bias, void* q_out, void* k_cache, void* v_cache,
+                                               const int32_t* tok_batch, const int32_t* tok_pos, int tokens, int heads, int dh,
+                                               int rotary_dim, int max_len, void* stream)
+{
+    FTCF_REQUIRE(tokens > 0 && heads > 0, FTCF_ERR_INVALID, "prefill scatter: empty");
+    FTCF_REQUIRE(rotary_dim % 2 == 0 && rotary_dim <= dh, FTCF_ERR_INVALID, "prefill scatter: rotary_dim %d", rotary_dim);
+    const dim3 grid(tokens, heads);
+#define FTCF_PS(DH_)                                                                                                   \
+    prefill_qkv_rotary_scatter_kernel<DH_><<<grid, DH_, 0, as_stream(stream)>>>(                                       \
+        static_cast<const __half*>(qkv), static_cast<const __half*>(qkv_bias), static_cast<__half*>(q_out),            \
+        static_cast<__half*>(k_cache), static_cast<__half*>(v_cache), tok_batch, tok_pos, heads, rotary_dim, max_len)
+    switch (dh) {
+        case 64: FTCF_PS(64); break;
+        case 128: FTCF_PS(128); break;
+        case 256: FTCF_PS(256); break;
+        default: FTCF_REQUIRE(false, FTCF_ERR_UNSUPPORTED, "prefill scatter: size_per_head %d", dh);
+    }
+#undef FTCF_PS
+    FTCF_LAUNCH_CHECK();
+    return FTCF_OK;
+}
+
+extern "C" int ftcf_prefill_attention(const void* q, const void* k_cache, const void* v_cache, void* ctx,
+                                      const int32_t* seq_offsets, int batch, int max_seq, int heads, int dh, int max_len,
+                                      float scale, void* stream)
+{
+    FTCF_REQUIRE(batch > 0 && max_seq > 0 && heads > 0, FTCF_ERR_INVALID, "prefill attention: empty");
+    const dim3 grid(ceil_div(max_seq, 32), heads, batch);
+#define FTCF_PA(DH_)                                                                                                   \
+    prefill_attention_kernel<DH_><<<grid, 128, 0, as_stream(stream)>>>(                                                \
+        static_cast<const __half*>(q), static_cast<const __half*>(k_cache), static_cast<const __half*>(v_cache),       \
+        static_cast<__half*>(ctx), seq_offsets, heads, max_len, scale)
+    switch (dh) {
+        case 64: FTCF_PA(64); break;
+        case 128: FTCF_PA(128); break;
+        default: FTCF_REQUIRE(false, FTCF_ERR_UNSUPPORTED, "prefill attention: size_per_head %d (supported: 64, 128)", dh);
+    }
+#undef FTCF_PA
+    FTCF_LAUNCH_CHECK();
+    return FTCF_OK;
+}

@@ -1,0 +1,133 @@
+// Shared device/host helpers for the sm_100a kernels of libftcf.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/ftcf.h"
+
+namespace ftcf {
+
+// ---------------------------------------------------------------- error plumbing (host)
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launch_count;   // kernels launched by this library (bench's gpu_launches)
+
+#define FTCF_CUDA_CHECK(expr)                                                                         \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            ::ftcf::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return FTCF_ERR_CUDA;                                                                     \
+        }                                                                                             \
+    } while (0)
+
+#define FTCF_LAUNCH_CHECK()                                                                           \
+    do {                                                                                              \
+        ::ftcf::g_launch_count.fetch_add(1, std::memory_order_relaxed);                               \
+        cudaError_t _e = cudaPeekAtLastError();                                                       \
+        if (_e != cudaSuccess) {                                                                      \
+            ::ftcf::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return FTCF_ERR_CUDA;                                                                     \
+        }                                                                                             \
+    } while (0)
+
+#define FTCF_REQUIRE(cond, code, ...)                                                                 \
+    do {                                                                                              \
+        if (!(cond)) {                                                                                \
+            ::ftcf::set_error(__VA_ARGS__);                                                           \
+            return code;                                                                              \
+        }                                                                                             \
+    } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+__host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum of one float; `red` is >= 32 floats of shared memory.  All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : 0.f;
+    return warp_sum(r);
+}
+__device__ __forceinline__ float block_max(float v, float* red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : -INFINITY;
+    return warp_max(r);
+}
+
+// 128-bit streaming load that does not allocate in L1 (weights / KV are touched once per launch).
+__device__ __forceinline__ uint4 ld_stream_16(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+// 128-bit cached read-only load (activations re-read by many warps).
+__device__ __forceinline__ uint4 ld_ro_16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+__device__ __forceinline__ float2 h2_to_f2(uint32_t u)
+{
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+__device__ __forceinline__ uint32_t f2_to_h2(float a, float b)
+{
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// tanh-form GELU in fp32: x * 0.5 * (1 + tanh(0.79788456 * (x + 0.044715 x^3))).  tanh through exp so that the
+// result is within a few ulp of the exact function (the reference uses a fast tanh in the int8 epilogue,
+// cutlass_extensions/epilogue/thread/ft_fused_activations.h:61-84).
+__device__ __forceinline__ float tanh_accurate(float x)
+{
+    const float ax = fabsf(x);
+    const float e = __expf(-2.f * ax);
+    const float t = __fdividef(1.f - e, 1.f + e);
+    return copysignf(t, x);
+}
+__device__ __forceinline__ float gelu_tanh_f32(float x)
+{
+    return x * (0.5f * (1.f + tanh_accurate(0.7978845608028654f * (x + 0.044715f * x * x * x))));
+}
+// fp16 path of the reference (kernels/activation_kernels.cu:59-72): cube and product rounded to half.
+__device__ __forceinline__ __half gelu_tanh_half_ref(__half v)
+{
+    const __half v2 = __hmul(v, v);
+    const __half pow3 = __hmul(v, v2);
+    const float vf = __half2float(v);
+    const float cdf = 0.5f * (1.f + tanh_accurate(0.7978845608028654f * (vf + 0.044715f * __half2float(pow3))));
+    return __hmul(v, __float2half_rn(cdf));
+}
+#endif  // __CUDACC__
+
+}  // namespace ftcf

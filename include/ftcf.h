@@ -1,0 +1,237 @@
+/*
+ * ftcf.h -- C ABI of libftcf.so, the B200 (sm_100a) engine behind the CodeFuse / GPT-NeoX path.
+ *
+ * This is the drop-in boundary below the reference's Python surface: the two pybind11 modules
+ * `libth_gptneox` (GptNeoXOp, reference src/fastertransformer/th_op/gptneox/GptNeoXOp.cc:190-212) and
+ * `libth_common` (symmetric_quantize_last_axis_of_batched_matrix_int8, reference
+ * src/fastertransformer/th_op/common/WeightOnlyQuantOps.cc:344-349) are thin torch-facing shims over the
+ * entry points declared here.  Plain pointers and sizes only; no torch / C++ types cross this line.
+ *
+ * Conventions
+ *   - every function returns 0 (FTCF_OK) or a non-zero ftcf_status; ftcf_last_error() gives the message
+ *     (thread-local).  Nothing here falls back to a CPU path: without a usable sm_100 device the calls fail.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - fp16 buffers are passed as void* (IEEE binary16, row-major); ids / lengths are int32.
+ *   - device pointers unless the name ends in _host.
+ *
+ * Each entry cites the reference interface it stands in for (paths relative to
+ * /root/reference/src/fastertransformer).
+ */
+#ifndef FTCF_H_
+#define FTCF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    FTCF_OK = 0,
+    FTCF_ERR_INVALID = 1,     /* bad argument (the binding turns it into a Python RuntimeError)       */
+    FTCF_ERR_CUDA = 2,        /* CUDA runtime / driver error                                          */
+    FTCF_ERR_NCCL = 3,        /* NCCL error                                                           */
+    FTCF_ERR_UNSUPPORTED = 4  /* shape or feature outside what the sm_100a kernels implement          */
+} ftcf_status;
+
+const char* ftcf_last_error(void);
+/* Library/ABI version, bumped when a signature changes. */
+int ftcf_abi_version(void);
+/* 0 when the current device is compute capability 10.x and the kernels in this build can run on it. */
+int ftcf_device_check(void);
+/* Kernels (and NCCL collectives) launched by this library in this process so far. */
+long long ftcf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight-only INT8 quantiser (CPU).  Replaces ft::symmetric_quantize<half,half|float> +
+ * preprocess_weights_for_mixed_gemm, kernels/cutlass_kernels/cutlass_preprocessors.cc:577-673,500-539,
+ * reached through th_op/common/WeightOnlyQuantOps.cc:140-233.
+ *   weight      [e, k, n] (e = 1 for a 2-D matrix), dtype: 0 = fp32, 1 = fp16, 2 = bf16, host memory
+ *   processed   e*k*n bytes: B200 layout = W^T, i.e. [e][n][k] with k contiguous, value q + 128 as uint8
+ *   unprocessed optional (may be NULL) plain int8 [e, k, n]
+ *   scales      [e, n] in the weight's dtype (absmax / 128, rounded to that dtype)
+ * The same rounding as the reference: q = clip(round_half_away(w / scale_fp32), -128, 127).
+ * ---------------------------------------------------------------------------------------------- */
+int ftcf_symmetric_quantize_int8_host(const void* weight_host, int dtype, size_t e, size_t k, size_t n,
+                                      uint8_t* processed_host, int8_t* unprocessed_host, void* scales_host);
+/* Layout helpers (CPU): plain int8 [k,n] <-> B200 layout, and the reference's sm80 ("Ampere") *.q.bin layout
+ * (cutlass_preprocessors.cc:133-201,207-348,350-370,437-498) -> B200 layout, for checkpoints made by the
+ * reference's quant_and_save.py. */
+int ftcf_int8_plain_to_b200_host(const int8_t* q_kn, size_t k, size_t n, uint8_t* out_nk);
+int ftcf_int8_ampere_to_b200_host(const int8_t* processed_ampere, size_t k, size_t n, uint8_t* out_nk);
+
+/* ------------------------------------------------------------------------------------------------
+ * Kernels.  One launcher per kernel family; all asynchronous on `stream`.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* y[m,n] = act(x[m,k] . dequant(W)[k,n] + bias), W given as W^T uint8 [n,k] (value q+128), per-column fp16 scale.
+ * fp32 accumulate, scale applied in the epilogue, fp16 out.  act: 0 none, 1 tanh-GELU.  bias may be NULL.
+ * Replaces CutlassFpAIntBGemmRunner<half,uint8_t>::gemm / gemm_bias_act,
+ * kernels/cutlass_kernels/fpA_intB_gemm/fpA_intB_gemm_template.h:461-570.
+ * impl: 0 = auto, 1 = force the skinny (m <= 32 streaming) kernel, 2 = force the tcgen05 kernel. */
+int ftcf_gemm_w8a16(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n,
+                    int k, int act, int impl, void* stream);
+
+/* y[m,n] = x[m,k] . W, W given K-major as W^T fp16 [n,k]; fp32 accumulate.  out_f32 = 1 writes fp32 (LM head
+ * logits, models/gptneox/GptNeoX.cc:869-912), else fp16 with optional bias + tanh-GELU applied with the
+ * reference's fp16 rounding points (layers/FfnLayer.cc:294-309, kernels/activation_kernels.cu:50-72).
+ * ldy = row pitch of y in elements.  Replaces cublasMMWrapper::Gemm, utils/cublasMMWrapper.cc:154-328. */
+int ftcf_gemm_f16(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
+                  int out_f32, int impl, void* stream);
+
+/* out[k,n] -> out_t[n,k] fp16 transpose (load-time re-layout of fp16 weights to K-major). */
+int ftcf_transpose_f16(const void* in_kn, void* out_nk, int k, int n, void* stream);
+
+/* LayerNorm, fp32 statistics and fp16 normalisation as kernels/layernorm_kernels.cu:158-286 (invokeGeneralLayerNorm
+ * :1653-1735).  Optional fused pre-add: if `residual_out` != NULL first computes
+ * residual_out = x + add1 (+ add_bias) in fp16 (invokeGeneralAddBiasResidualPreLayerNorm), then normalises it. */
+int ftcf_layernorm(const void* x, const void* gamma, const void* beta, void* y, int m, int n, float eps, void* stream);
+int ftcf_add_bias_residual_layernorm(const void* x, const void* add1, const void* add_bias, void* residual_out,
+                                     const void* gamma, const void* beta, void* y, int m, int n, float eps,
+                                     void* stream);
+
+/* out = (half)(x / tp) + ffn + attn + bias   (fp16 adds, kernels/add_residual_kernels.cu:116-176)
+ * and  out = x + y + bias                     (invokeAddBiasResidual, sequential-residual path). */
+int ftcf_add_bias_attn_ffn_residual(void* out, const void* ffn, const void* attn, const void* x, const void* bias,
+                                    int m, int n, int tp, void* stream);
+int ftcf_add_bias_residual(void* out, const void* y, const void* x, const void* bias, int m, int n, void* stream);
+
+/* Row gather from the embedding table (kernels/gpt_kernels.cu:32-105, decoding_kernels.cu:260).
+ * ids[i] for i < m; ids_stride lets the caller point into a time-major id buffer. */
+int ftcf_embedding_lookup(void* out, const void* table, const int32_t* ids, int m, int n, int vocab, void* stream);
+
+/* Decode attention for one new token per sequence (masked_multihead_attention_kernel,
+ * kernels/decoder_masked_multihead_attention/decoder_masked_multihead_attention_template.hpp:1099-1919;
+ * parameter block kernels/decoder_masked_multihead_attention.h:51-158). */
+typedef struct {
+    const void* qkv;            /* [B, 3*heads*dh] fp16: q | k | v, each [heads, dh]                          */
+    const void* qkv_bias;       /* [3*heads*dh] fp16 or NULL                                                  */
+    void* k_cache;              /* [B, heads, max_len, dh] fp16 (this layer, this rank)                       */
+    void* v_cache;              /* [B, heads, max_len, dh] fp16                                               */
+    void* ctx;                  /* [B, heads*dh] fp16 out                                                     */
+    const int32_t* seq_len;     /* [B] cache slot of the new token == number of earlier slots                 */
+    const int32_t* input_len;   /* [B] prompt lengths: slots [input_len, max_input_len) are the masked pad gap */
+    const int32_t* pad_count;   /* [B] total_padding_tokens (rotary position = timestep - pad_count)          */
+    const uint8_t* finished;    /* [B] or NULL; finished rows are skipped (template.hpp:1176-1178)            */
+    const int32_t* step;        /* device scalar: the loop's `step`; timestep = step - 1                      */
+    float* partial;             /* split-KV scratch [B*heads*splits*(dh+2)] fp32 (unused when splits == 1)    */
+    int32_t* counters;          /* [B*heads] zero-initialised, self-resetting                                 */
+    int32_t batch, heads, dh, rotary_dim, max_len, max_input_len, splits;
+    float inv_sqrt_dh;
+} ftcf_mmha_params;
+int ftcf_mmha_decode(const ftcf_mmha_params* p, void* stream);
+/* Scratch sizing / split choice for ftcf_mmha_decode. */
+int ftcf_mmha_choose_splits(int batch, int heads, int max_len);
+
+/* Prefill: qkv + bias, NeoX rotary at the token's position, q kept, k/v scattered into the cache
+ * (add_fusedQKV_bias_transpose_kernel + transpose_4d_batch_major_{k,v}_cache,
+ * kernels/unfused_attention_kernels.cu:1326-1484,1673-1757), on padding-removed tokens. */
+int ftcf_prefill_qkv_rotary_scatter(const void* qkv, const void* qkv_bias, void* q_out, void* k_cache, void* v_cache,
+                                    const int32_t* tok_batch, const int32_t* tok_pos, int tokens, int heads, int dh,
+                                    int rotary_dim, int max_len, void* stream);
+/* Causal attention over each sequence's own prompt (replaces the unfused QK^T / softmax / PV chain,
+ * layers/attention_layers/GptContextAttentionLayer.cc:194-300).  q [T, heads, dh]; ctx [T, heads*dh]. */
+int ftcf_prefill_attention(const void* q, const void* k_cache, const void* v_cache, void* ctx,
+                           const int32_t* seq_offsets /* [B+1] */, int batch, int max_seq, int heads, int dh,
+                           int max_len, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampling stack on fp32 logits (layers/DynamicDecodeLayer.cc:192-495, sampling_layers/TopKSamplingLayer.cu).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    float* logits;                 /* [B, vocab_padded] fp32, modified in place                              */
+    int32_t* output_ids;           /* [max_len, B] time-major                                                */
+    int32_t* seq_len;              /* [B]                                                                    */
+    uint8_t* finished;             /* [B]                                                                    */
+    float* cum_log_probs;          /* [B] or NULL                                                            */
+    const int32_t* input_len;      /* [B]                                                                    */
+    const int32_t* top_k;          /* [B] runtime k (already through the setup rules)                        */
+    const float* top_p;            /* [B]                                                                    */
+    const float* temperature;      /* [B] or NULL (NULL == all 1)                                            */
+    const float* repetition_penalty; /* [B] or NULL                                                          */
+    const int32_t* optional_last_tokens; /* [B, n_last] (-1 padded) or NULL; applied when step == max_input_len */
+    const int32_t* stop_words;     /* [B, 2, n_stop] or NULL                                                 */
+    void* curand_states;           /* [B] curandState_t                                                      */
+    int32_t* step;                 /* device scalar, read; incremented by ftcf_sampling_advance              */
+    int32_t* finished_count_host_mapped; /* device-visible pinned int (or NULL): #finished after this step   */
+    void* workspace;               /* ftcf_sampling_workspace_bytes()                                        */
+    int32_t batch, vocab, vocab_padded, max_top_k, n_last, n_stop, max_input_len, max_len, end_id;
+    int32_t want_probs;            /* 1: softmax before top-k and accumulate cum_log_probs                   */
+} ftcf_sampling_params;
+size_t ftcf_sampling_workspace_bytes(int batch, int vocab_padded, int max_top_k);
+size_t ftcf_curand_state_bytes(void);
+/* curand_init(seed[b], 0, 0) per row (kernels/sampling_topk_kernels.cu:32-55). */
+int ftcf_curand_init(void* states, const uint64_t* seeds, int batch, void* stream);
+/* One decoding step of logit post-processing + top-k sampling + stop criteria; advances *step by one at the end. */
+int ftcf_sampling_step(const ftcf_sampling_params* p, void* stream);
+/* gatherTree for beam 1: time-major ids -> [B, max_len] with the pad gap removed (kernels/decoding_kernels.cu:452-580). */
+int ftcf_gather_output(int32_t* out /* [B, max_len] */, int32_t* out_len /* [B] */, const int32_t* ids_time_major,
+                       const int32_t* seq_len, const int32_t* input_len, int batch, int max_input_len, int max_len,
+                       int end_id, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model-level engine: the request loop of ft::GptNeoX<T>::forward (models/gptneox/GptNeoX.cc:385-1052) with
+ * GptNeoXContextDecoder (…ContextDecoder.cc:223-512) and GptNeoXDecoder (…Decoder.cc:197-389) underneath.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ftcf_gptneox ftcf_gptneox;
+
+typedef struct {
+    int32_t head_num, size_per_head, inter_size, layer_num, vocab_size, rotary_embedding_dim;
+    int32_t start_id, end_id;
+    int32_t tensor_para_size, tensor_para_rank;
+    int32_t int8_mode;            /* 0: fp16 weights, 1: weight-only int8                                    */
+    int32_t use_gptj_residual;    /* 1: parallel residual                                                    */
+    float layernorm_eps;          /* 1e-5 (models/gptneox/GptNeoX.h:42-43)                                   */
+    int32_t int8_layout;          /* 0: B200 layout (ours), 1: plain int8 [k,n] (re-laid out on the device)  */
+} ftcf_gptneox_config;
+
+/* weights: 12*L+4 fp16 device pointers in GptNeoXOp order (th_op/gptneox/GptNeoXOp.h:121-174); int8_weights and
+ * scales: 4*L each ({qkv,o,ffn1,ffn2}*L + layer), NULL entries allowed when int8_mode == 0.
+ * nccl_unique_id: 128 bytes from ftcf_nccl_unique_id (same on all ranks) or NULL when tensor_para_size == 1. */
+int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config* cfg, const void* const* weights,
+                        size_t n_weights, const void* const* int8_weights, const void* const* scales, size_t n_int8,
+                        const void* nccl_unique_id, void* stream);
+void ftcf_gptneox_destroy(ftcf_gptneox* h);
+int ftcf_nccl_unique_id(void* out128);
+
+typedef void (*ftcf_token_callback)(void* user, int32_t step, const int32_t* last_tokens_host /* [B] */,
+                                    const int32_t* idxs_host /* [B] */, int32_t batch);
+typedef struct {
+    const int32_t* input_ids;       /* device [B, S]                                                         */
+    const int32_t* input_lengths;   /* device [B]                                                            */
+    int32_t batch, max_input_len, output_len;
+    /* sampling arguments on the HOST, each either NULL, 1 element or B elements (n_* gives the count)       */
+    const int32_t* top_k_host;  int32_t n_top_k;
+    const float* top_p_host;    int32_t n_top_p;
+    const float* temperature_host; int32_t n_temperature;
+    const float* repetition_penalty_host; int32_t n_repetition_penalty;
+    const int64_t* random_seed_host; int32_t n_random_seed;
+    const int32_t* stop_words;      /* device [B, 2, n_stop] or NULL */ int32_t n_stop;
+    const int32_t* optional_last_tokens; /* device [B, n_last] or NULL */ int32_t n_last;
+    int32_t return_cum_log_probs;
+    ftcf_token_callback callback;   /* may be NULL */ void* callback_user;
+    /* outputs (device) */
+    int32_t* output_ids;            /* [B, 1, S + output_len]                                                */
+    int32_t* sequence_lengths;      /* [B, 1]                                                                */
+    float* cum_log_probs;           /* [B, 1] or NULL                                                        */
+    /* optional debug taps (device, may be NULL): fp32 logits of every step [steps, B, vocab]                */
+    float* logits_trace;  int32_t logits_trace_steps;
+} ftcf_gptneox_request;
+
+typedef struct {
+    int32_t steps;                  /* decode-loop iterations executed                                       */
+    float prefill_ms, decode_ms;    /* CUDA-event times of the two phases                                    */
+    int64_t kernel_launches;        /* kernels launched by this request                                      */
+} ftcf_gptneox_stats;
+
+int ftcf_gptneox_forward(ftcf_gptneox* h, const ftcf_gptneox_request* req, ftcf_gptneox_stats* stats);
+/* Per-step decode times (ms) of the last request, up to n entries; returns the count written. */
+int ftcf_gptneox_last_step_ms(ftcf_gptneox* h, float* out, int n);
+/* Engine options: "cuda_graph" (0/1), "gemm_impl" (0 auto / 1 skinny / 2 tcgen05), "step_timing" (0/1). */
+int ftcf_gptneox_set_option(ftcf_gptneox* h, const char* name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FTCF_H_ */

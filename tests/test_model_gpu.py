@@ -1,0 +1,139 @@
+"""End-to-end parity of the engine (GptNeoXOp mirror over the C ABI) against the oracle model on small configurations.
+
+Token ids must match exactly (greedy and seeded top-k); raw logits of every step are compared within an fp16-level
+tolerance that is stated here: |dlogit| <= 3e-2 + 2e-2 |logit| (logits of these models are O(0.3); the chain runs
+2-3 layers of fp16-rounded activations with fp32 accumulation whose summation order differs from the oracle's).
+"""
+import numpy as np
+import pytest
+import torch
+
+from fastertransformer4codefuse_b200 import weights as W
+from fastertransformer4codefuse_b200.gptneox_op import GptNeoXOp
+from helpers import assert_close, oracle_from_rank_weights, tiny_cfg, to_cuda_lists
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_RTOL, LOGIT_ATOL = 2e-2, 3e-2
+
+
+def _build(cfg, int8_mode, cuda, seed=0):
+    rw = W.make_synthetic(cfg, 1, 0, int8_mode, "cpu", seed=seed, keep_plain=True)
+    ref = oracle_from_rank_weights(cfg, [rw], int8_mode)
+    w, q, s = to_cuda_lists(rw, cuda)
+    op = GptNeoXOp(None, 0, cfg.head_num, cfg.size_per_head, cfg.inter_size, cfg.layer_num, cfg.vocab_size,
+                   cfg.rotary_embedding_dim, cfg.start_id, cfg.end_id, 1, 1, int8_mode, 1024, cfg.use_gptj_residual, w, q, s)
+    return op, ref
+
+
+def _prompts(B, S, V, lens, seed=1234):
+    g = np.random.default_rng(seed)
+    ids = g.integers(0, V - 1, size=(B, S)).astype(np.int32)
+    for b, n in enumerate(lens):
+        ids[b, n:] = V - 1          # right-padded with end_id (codefuse_example.py:700)
+    return ids
+
+
+def _compare(op, ref, cuda, ids, lens, out_len, graph, **kw):
+    B, S = ids.shape
+    V = ref.cfg.vocab_size
+    op.set_option("cuda_graph", 1 if graph else 0)
+    trace = torch.zeros(out_len, B, V, dtype=torch.float32, device=cuda) if not graph else None
+    t = lambda a, dt: None if a is None else torch.tensor(np.asarray(a), dtype=dt)
+    res = op.forward(torch.from_numpy(ids).to(cuda), torch.tensor(lens, dtype=torch.int32, device=cuda), out_len, 1,
+                     t(kw.get("top_k"), torch.int32), t(kw.get("top_p"), torch.float32), None, t(kw.get("temperature"), torch.float32),
+                     None, t(kw.get("repetition_penalty"), torch.float32), t(kw.get("random_seed"), torch.int64), None, None,
+                     kw.get("return_cum_log_probs", 0), None, logits_trace=trace)
+    exp = ref.forward(ids, lens, out_len, top_k=kw.get("top_k"), top_p=kw.get("top_p"), temperature=kw.get("temperature"),
+                      repetition_penalty=kw.get("repetition_penalty"), random_seed=kw.get("random_seed"),
+                      return_cum_log_probs=kw.get("return_cum_log_probs", 0), keep_logits=True)
+    if trace is not None:
+        for i, lg in enumerate(exp["logits"]):
+            assert_close(f"logits step {i}", trace[i].cpu().numpy(), lg, LOGIT_RTOL, LOGIT_ATOL)
+    assert np.array_equal(res[0].cpu().numpy(), exp["output_ids"]), (res[0].cpu().numpy(), exp["output_ids"])
+    assert np.array_equal(res[1].cpu().numpy(), exp["sequence_lengths"])
+    if kw.get("return_cum_log_probs", 0):
+        np.testing.assert_allclose(res[2].cpu().numpy(), exp["cum_log_probs"], rtol=2e-2, atol=2e-2)
+    return res, exp
+
+
+@pytest.mark.parametrize("int8_mode", [0, 1])
+@pytest.mark.parametrize("graph", [False, True])
+def test_greedy_full_batch(cuda, int8_mode, graph):
+    cfg = tiny_cfg()
+    op, ref = _build(cfg, int8_mode, cuda)
+    ids = _prompts(2, 12, cfg.vocab_size, [12, 12])
+    _compare(op, ref, cuda, ids, [12, 12], 10, graph)
+
+
+@pytest.mark.parametrize("int8_mode", [0, 1])
+def test_greedy_ragged_batch(cuda, int8_mode):
+    cfg = tiny_cfg()
+    op, ref = _build(cfg, int8_mode, cuda, seed=3)
+    lens = [16, 5, 11, 1]
+    ids = _prompts(4, 16, cfg.vocab_size, lens, seed=7)
+    _compare(op, ref, cuda, ids, lens, 8, False)
+    _compare(op, ref, cuda, ids, lens, 8, True)
+
+
+def test_sequential_residual(cuda):
+    cfg = tiny_cfg(use_gptj_residual=False)
+    op, ref = _build(cfg, 1, cuda, seed=5)
+    lens = [9, 4]
+    ids = _prompts(2, 9, cfg.vocab_size, lens, seed=9)
+    _compare(op, ref, cuda, ids, lens, 6, False)
+
+
+def test_dh128_full_rotary(cuda):
+    cfg = tiny_cfg(head_num=2, size_per_head=128, rotary_embedding_dim=128, inter_size=1024, layer_num=3)
+    op, ref = _build(cfg, 1, cuda, seed=11)
+    lens = [20, 13]
+    ids = _prompts(2, 20, cfg.vocab_size, lens, seed=2)
+    _compare(op, ref, cuda, ids, lens, 12, False)
+    _compare(op, ref, cuda, ids, lens, 12, True)
+
+
+def test_seeded_topk_sampling_and_cum_log_probs(cuda):
+    cfg = tiny_cfg()
+    op, ref = _build(cfg, 1, cuda, seed=1)
+    lens = [10, 7, 10]
+    ids = _prompts(3, 10, cfg.vocab_size, lens, seed=4)
+    _compare(op, ref, cuda, ids, lens, 8, False, top_k=[8, 8, 8], top_p=[0.9, 0.9, 0.9], temperature=[0.7, 0.7, 0.7],
+             repetition_penalty=[1.1, 1.1, 1.1], random_seed=[42, 42, 43], return_cum_log_probs=1)
+
+
+def test_single_token_prompt_runs_decoder_only(cuda):
+    cfg = tiny_cfg()
+    op, ref = _build(cfg, 1, cuda, seed=2)
+    ids = _prompts(2, 1, cfg.vocab_size, [1, 1], seed=3)
+    _compare(op, ref, cuda, ids, [1, 1], 6, False)
+
+
+def test_streaming_callback_and_early_stop(cuda):
+    cfg = tiny_cfg()
+    op, ref = _build(cfg, 1, cuda, seed=6)
+    lens = [6, 6]
+    ids = _prompts(2, 6, cfg.vocab_size, lens, seed=8)
+    msgs = []
+    res = op.forward(torch.from_numpy(ids).to(cuda), torch.tensor(lens, dtype=torch.int32, device=cuda), 7, 1, None, None, None, None, None,
+                     None, None, None, None, 0, msgs.append)
+    exp = ref.forward(ids, lens, 7)
+    assert np.array_equal(res[0].cpu().numpy(), exp["output_ids"])
+    assert len(msgs) == 6                                     # every step but the last (GptNeoX.cc:1023-1029)
+    out = res[0].cpu().numpy()
+    for i, m in enumerate(msgs):
+        assert m["idxs"] == [[i], [i]]
+        assert m["last_tokens"] == [[int(out[0, 0, 6 + i])], [int(out[1, 0, 6 + i])]]
+
+
+def test_argument_errors_raise(cuda):
+    cfg = tiny_cfg()
+    op, _ = _build(cfg, 0, cuda)
+    ids = torch.zeros(1, 4, dtype=torch.int64, device=cuda)
+    with pytest.raises(RuntimeError):
+        op.forward(ids, torch.tensor([4], dtype=torch.int32, device=cuda), 4)
+    ids32 = torch.zeros(1, 4, dtype=torch.int32, device=cuda)
+    with pytest.raises(RuntimeError):
+        op.forward(ids32, torch.tensor([9], dtype=torch.int32, device=cuda), 4)      # length > max_input_length
+    with pytest.raises(RuntimeError):
+        op.forward(ids32, torch.tensor([4], dtype=torch.int32, device=cuda), 4, 3)   # beam search not there yet
