@@ -153,7 +153,9 @@ using namespace ftcf;
 
 struct ftcf_gptneox {
     ftcf_gptneox_config cfg{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;          // the engine's own non-blocking stream: all work (and the captured graph) runs here
+    cudaStream_t caller_stream = nullptr;   // the stream handed in at construction (torch's current stream, GptNeoXOp.h:180)
+    cudaEvent_t caller_ev = nullptr;
     int h = 0, Hl = 0, hl = 0, inter_l = 0, Vp = 0, Vl = 0, t = 1, rank = 0;
     std::vector<LayerW> layers;
     const __half *wte = nullptr, *lnf_g = nullptr, *lnf_b = nullptr, *lm_head = nullptr;
@@ -279,7 +281,17 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
 
     auto* e = new ftcf_gptneox();
     e->cfg = c;
-    e->stream = as_stream(stream);
+    e->caller_stream = as_stream(stream);
+    // Stream capture is not allowed on the legacy default stream, which is what torch hands over by default, so the
+    // engine owns a stream and orders it after the caller's with an event at the start of every request.
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->caller_ev, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("create: cannot create the engine stream");
+        delete e;
+        return FTCF_ERR_CUDA;
+    }
+    cudaEventRecord(e->caller_ev, e->caller_stream);
+    cudaStreamWaitEvent(e->stream, e->caller_ev, 0);
     e->t = t;
     e->rank = c.tensor_para_rank;
     e->h = c.head_num * c.size_per_head;
@@ -380,6 +392,8 @@ extern "C" void ftcf_gptneox_destroy(ftcf_gptneox* e)
     if (e->host_flag) cudaFreeHost(e->host_flag);
     if (e->host_stage) cudaFreeHost(e->host_stage);
     if (e->comm && g_nccl.ok) g_nccl.CommDestroy(e->comm);
+    if (e->caller_ev) cudaEventDestroy(e->caller_ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
 
@@ -479,6 +493,8 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     FTCF_REQUIRE(r.input_ids && r.input_lengths && r.output_ids && r.sequence_lengths, FTCF_ERR_INVALID, "forward: null tensor");
     const int max_len = S + out_len;
     cudaStream_t st = e->stream;
+    FTCF_CUDA_CHECK(cudaEventRecord(e->caller_ev, e->caller_stream));   // inputs were produced on the caller's stream
+    FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->caller_ev, 0));
     const long long launches0 = g_launch_count.load();
     const int dh = c.size_per_head, L = c.layer_num;
 

@@ -76,7 +76,7 @@ layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ add1, 
             __half2* vh = reinterpret_cast<__half2*>(&v[i]);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                vh[j] = __hadd2(__hmul2(__hmul2(__hsub2(vh[j], mean_h), rstd_h), gh[j]), bh[j]);
+                vh[j] = __hadd2_rn(__hmul2_rn(__hmul2_rn(__hsub2_rn(vh[j], mean_h), rstd_h), gh[j]), bh[j]);   // _rn: no mul+add contraction, every step rounds (oracle layernorm_ref)
             *reinterpret_cast<uint4*>(y + row * n + vi * 8) = v[i];
         }
     }

@@ -317,3 +317,57 @@ def test_prefill_scatter_and_attention(lib, cuda, Dh, rot):
         assert_close("prefill k cache", kc[b, :, :e - s].float().cpu(), k[s:e].transpose(0, 1), rtol=2e-3, atol=1e-3)
         assert torch.equal(vc[b, :, :e - s].float().cpu(), v[s:e].transpose(0, 1))
     assert_close("prefill ctx", ctx.float().cpu(), ctx_ref.reshape(T, hl), rtol=5e-3, atol=2e-3)
+
+
+# ------------------------------------------------------------------ tcgen05 kernels (impl = 2)
+@pytest.mark.parametrize("m", [1, 16, 17, 33, 64, 100, 128, 129, 300])
+@pytest.mark.parametrize("n,k", [(256, 128), (1024, 4096), (5120, 640), (200, 256)])
+def test_w8a16_tcgen05_grid(lib, cuda, m, n, k):
+    torch.manual_seed(734876213 + m + n)
+    w = (torch.randn(k, n, device=cuda) * 0.002).half()
+    p, s, q = _quant(w)
+    x = torch.randn(m, k, device=cuda).half()
+    y = _gemm_w8(lib, x, p, s, None, m, n, k, 0, impl=2)
+    ref = x.float() @ (q.float() * s.float()[None, :])
+    assert_close(f"tcgen05 w8a16 m={m} n={n} k={k}", y.float().cpu(), ref.cpu(), rtol=1e-3, atol=2e-3)
+
+
+def test_w8a16_tcgen05_exact_dequant_round_trip(lib, cuda):
+    torch.manual_seed(1)
+    k, n = 256, 384
+    w = (torch.randn(k, n, device=cuda) * 0.002).half()
+    p, s, q = _quant(w)
+    x = torch.eye(k, dtype=torch.float16, device=cuda)
+    y = _gemm_w8(lib, x, p, s, None, k, n, k, 0, impl=2)
+    assert torch.equal(y, (q.float() * s.float()[None, :]).half())
+
+
+@pytest.mark.parametrize("m", [40, 256])
+def test_w8a16_tcgen05_bias_gelu(lib, cuda, m):
+    torch.manual_seed(11 + m)
+    n, k = 2048, 1024
+    w = (torch.randn(k, n, device=cuda) * 0.02).half()
+    p, s, q = _quant(w)
+    x = torch.randn(m, k, device=cuda).half()
+    bias = (torch.randn(n, device=cuda) * 0.1).half()
+    y = _gemm_w8(lib, x, p, s, bias, m, n, k, 1, impl=2)
+    acc = x.float() @ (q.float() * s.float()[None, :]) + bias.float()
+    ref = torch.nn.functional.gelu(acc, approximate="tanh")
+    assert_close(f"tcgen05 w8a16 gelu m={m}", y.float().cpu(), ref.cpu(), rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("m", [8, 40, 200])
+@pytest.mark.parametrize("out_f32", [0, 1])
+def test_f16_tcgen05(lib, cuda, m, out_f32):
+    torch.manual_seed(5 + m)
+    n, k = 1008, 768
+    w_nk = (torch.randn(n, k, device=cuda) * 0.02).half()
+    x = torch.randn(m, k, device=cuda).half()
+    y = torch.empty(m, n, dtype=torch.float32 if out_f32 else torch.float16, device=cuda)
+    capi.check(lib.ftcf_gemm_f16(x.data_ptr(), w_nk.data_ptr(), None, y.data_ptr(), m, n, k, n, 0, out_f32, 2, stream()))
+    torch.cuda.synchronize()
+    ref = x.float() @ w_nk.float().t()
+    if out_f32:
+        assert_close("tcgen05 f16 gemm fp32 out", y.cpu(), ref.cpu(), rtol=1e-4, atol=1e-4)
+    else:
+        assert_close("tcgen05 f16 gemm fp16 out", y.float().cpu(), ref.cpu(), rtol=1e-3, atol=1e-3)
