@@ -96,32 +96,40 @@ def cpu_baseline(sample_layers=(2, 4), in_len=16, out_len=8):
     h = MODEL["head_num"] * MODEL["size_per_head"]
     per_tok = {}
     t_all0 = time.perf_counter()
-    for nl in sample_layers:
-        cfg = GPTNeoXConfig(hidden_size=h, num_hidden_layers=nl, num_attention_heads=MODEL["head_num"],
-                            intermediate_size=MODEL["inter_size"], vocab_size=MODEL["vocab_size"], hidden_act="gelu_new",
-                            use_parallel_residual=True, max_position_embeddings=2048, rotary_pct=1.0, tie_word_embeddings=False)
-        with torch.device("meta"):
-            model = GPTNeoXForCausalLM(cfg)
-        model = model.to_empty(device="cpu")
-        with torch.no_grad():
-            for p in model.parameters():
-                p.normal_(0.0, 0.02)
-            for name, b in model.named_buffers():
-                if "inv_freq" in name:
-                    dim = b.shape[0] * 2
-                    b.copy_(1.0 / (10000 ** (torch.arange(0, dim, 2, dtype=torch.float32) / dim)))
-        model.eval()
-        ids = torch.randint(0, MODEL["vocab_size"], (1, in_len), generator=torch.Generator().manual_seed(1234))
+    nl_max = max(sample_layers)
+    cfg = GPTNeoXConfig(hidden_size=h, num_hidden_layers=nl_max, num_attention_heads=MODEL["head_num"],
+                        intermediate_size=MODEL["inter_size"], vocab_size=MODEL["vocab_size"], hidden_act="gelu_new",
+                        use_parallel_residual=True, max_position_embeddings=2048, tie_word_embeddings=False)
+    with torch.device("meta"):
+        model = GPTNeoXForCausalLM(cfg)
+    model = model.to_empty(device="cpu")
+    with torch.no_grad():
+        for p in model.parameters():
+            p.normal_(0.0, 0.02)
+        for name, b in model.named_buffers():
+            if "inv_freq" in name:
+                dim = b.shape[0] * 2
+                b.copy_(1.0 / (10000 ** (torch.arange(0, dim, 2, dtype=torch.float32) / dim)))
+    model.eval()
+    all_layers = list(model.gpt_neox.layers)
+    ids = torch.randint(0, MODEL["vocab_size"], (1, in_len), generator=torch.Generator().manual_seed(1234))
+    # the SAME weights at both depths (the deeper model first, then its first layers only), three untimed tokens each
+    for nl in sorted(sample_layers, reverse=True):
+        model.gpt_neox.layers = torch.nn.ModuleList(all_layers[:nl])
+        model.config.num_hidden_layers = nl
         with torch.no_grad():
             out = model(ids, use_cache=True)                    # prefill
             past, nxt = out.past_key_values, out.logits[:, -1:].argmax(-1)
-            model(nxt, past_key_values=past, use_cache=True)    # warm-up token
+            for _ in range(3):
+                out = model(nxt, past_key_values=past, use_cache=True)
+                past, nxt = out.past_key_values, out.logits[:, -1:].argmax(-1)
             t0 = time.perf_counter()
             for _ in range(out_len):
                 out = model(nxt, past_key_values=past, use_cache=True)
                 past, nxt = out.past_key_values, out.logits[:, -1:].argmax(-1)
             per_tok[nl] = (time.perf_counter() - t0) / out_len
-        del model, out, past
+        del out, past
+    del model, all_layers
     a, b = sample_layers
     t_layer = max((per_tok[b] - per_tok[a]) / (b - a), 1e-9)
     t_fixed = max(per_tok[a] - a * t_layer, 0.0)

@@ -42,6 +42,10 @@ class SamplingParams(C.Structure):
     ]
 
 
+class PrefetchHint(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("n", C.c_int32), ("row_bytes", C.c_int32)]
+
+
 class GptNeoXConfig(C.Structure):
     _fields_ = [
         ("head_num", C.c_int32), ("size_per_head", C.c_int32), ("inter_size", C.c_int32), ("layer_num", C.c_int32),
@@ -82,6 +86,7 @@ SIGNATURES = {
     "ftcf_abi_version": (C.c_int, []),
     "ftcf_device_check": (C.c_int, []),
     "ftcf_launch_count": (C.c_longlong, []),
+    "ftcf_set_tunable": (C.c_int, [C.c_char_p, C.c_int]),
     "ftcf_symmetric_quantize_int8_host": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,
                                                     C.c_void_p, C.c_void_p]),
     "ftcf_int8_plain_to_b200_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
@@ -90,6 +95,10 @@ SIGNATURES = {
                                   C.c_int, C.c_int, C.c_void_p]),
     "ftcf_gemm_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_void_p]),
+    "ftcf_gemm_w8a16_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.POINTER(PrefetchHint), C.c_void_p]),
+    "ftcf_gemm_f16_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.POINTER(PrefetchHint), C.c_void_p]),
     "ftcf_transpose_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ftcf_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "ftcf_add_bias_residual_layernorm": (C.c_int, [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),
@@ -130,6 +139,11 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here == the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    # experiment hook: FTCF_TUNABLES="skinny_target_ctas=148,pdl=0"
+    for item in filter(None, os.environ.get("FTCF_TUNABLES", "").split(",")):
+        key, _, val = item.partition("=")
+        if lib.ftcf_set_tunable(key.strip().encode(), int(val)) != 0:
+            raise FtcfError(f"FTCF_TUNABLES: {lib.ftcf_last_error().decode()}")
     _lib = lib
     return lib
 

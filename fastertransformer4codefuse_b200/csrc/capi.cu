@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -13,6 +14,7 @@ namespace ftcf {
 
 static thread_local char g_err[1024] = "";
 std::atomic<long long> g_launch_count{0};
+std::atomic<int> g_pdl_enabled{1};
 
 void set_error(const char* fmt, ...)
 {
@@ -24,14 +26,15 @@ void set_error(const char* fmt, ...)
 
 // implemented in gemm_skinny.cu / gemm_tcgen05.cu
 int gemm_w8a16_skinny(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n, int k,
-                      int act, cudaStream_t st);
+                      int act, const ftcf_prefetch_hint* next, cudaStream_t st);
 int gemm_f16_skinny(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
-                    int out_f32, cudaStream_t st);
+                    int out_f32, const ftcf_prefetch_hint* next, cudaStream_t st);
 int gemm_w8a16_tcgen05(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n, int k,
                        int act, cudaStream_t st);
 int gemm_f16_tcgen05(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
                      int out_f32, cudaStream_t st);
 bool gemm_tcgen05_supported(int m, int n, int k, int elem_bytes);
+extern std::atomic<int> g_sk_target_ctas, g_sk_prefetch_rows;
 
 }  // namespace ftcf
 
@@ -40,6 +43,17 @@ using namespace ftcf;
 extern "C" const char* ftcf_last_error(void) { return g_err; }
 extern "C" int ftcf_abi_version(void) { return 1; }
 extern "C" long long ftcf_launch_count(void) { return g_launch_count.load(); }
+
+extern "C" int ftcf_set_tunable(const char* name, int value)
+{
+    FTCF_REQUIRE(name != nullptr, FTCF_ERR_INVALID, "set_tunable: null name");
+    const std::string n(name);
+    if (n == "pdl") g_pdl_enabled.store(value);
+    else if (n == "skinny_target_ctas") { FTCF_REQUIRE(value >= 1, FTCF_ERR_INVALID, "skinny_target_ctas %d", value); g_sk_target_ctas.store(value); }
+    else if (n == "skinny_prefetch_rows") { FTCF_REQUIRE(value >= 0, FTCF_ERR_INVALID, "skinny_prefetch_rows %d", value); g_sk_prefetch_rows.store(value); }
+    else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_tunable: unknown tunable %s", name);
+    return FTCF_OK;
+}
 
 extern "C" int ftcf_device_check(void)
 {
@@ -58,30 +72,42 @@ extern "C" int ftcf_device_check(void)
 // when the shape is one it supports.
 static constexpr int kSkinnyMaxM = 32;
 
-extern "C" int ftcf_gemm_w8a16(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n,
-                               int k, int act, int impl, void* stream)
+extern "C" int ftcf_gemm_w8a16_ex(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n,
+                                  int k, int act, int impl, const ftcf_prefetch_hint* next, void* stream)
 {
     FTCF_REQUIRE(x && w_nk && scale && y, FTCF_ERR_INVALID, "gemm_w8a16: null operand");
     FTCF_REQUIRE(act == 0 || act == 1, FTCF_ERR_INVALID, "gemm_w8a16: act %d", act);
     cudaStream_t st = as_stream(stream);
-    if (impl == 1) return gemm_w8a16_skinny(x, w_nk, scale, bias, y, m, n, k, act, st);
+    if (impl == 1) return gemm_w8a16_skinny(x, w_nk, scale, bias, y, m, n, k, act, next, st);
     if (impl == 2) return gemm_w8a16_tcgen05(x, w_nk, scale, bias, y, m, n, k, act, st);
     if (m > kSkinnyMaxM && gemm_tcgen05_supported(m, n, k, 1)) return gemm_w8a16_tcgen05(x, w_nk, scale, bias, y, m, n, k, act, st);
-    return gemm_w8a16_skinny(x, w_nk, scale, bias, y, m, n, k, act, st);
+    return gemm_w8a16_skinny(x, w_nk, scale, bias, y, m, n, k, act, next, st);
 }
 
-extern "C" int ftcf_gemm_f16(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
-                             int out_f32, int impl, void* stream)
+extern "C" int ftcf_gemm_w8a16(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n,
+                               int k, int act, int impl, void* stream)
+{
+    return ftcf_gemm_w8a16_ex(x, w_nk, scale, bias, y, m, n, k, act, impl, nullptr, stream);
+}
+
+extern "C" int ftcf_gemm_f16_ex(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
+                                int out_f32, int impl, const ftcf_prefetch_hint* next, void* stream)
 {
     FTCF_REQUIRE(x && w_nk && y, FTCF_ERR_INVALID, "gemm_f16: null operand");
     FTCF_REQUIRE(act == 0 || act == 1, FTCF_ERR_INVALID, "gemm_f16: act %d", act);
     FTCF_REQUIRE(ldy >= n, FTCF_ERR_INVALID, "gemm_f16: ldy %d < n %d", ldy, n);
     cudaStream_t st = as_stream(stream);
-    if (impl == 1) return gemm_f16_skinny(x, w_nk, bias, y, m, n, k, ldy, act, out_f32, st);
+    if (impl == 1) return gemm_f16_skinny(x, w_nk, bias, y, m, n, k, ldy, act, out_f32, next, st);
     if (impl == 2) return gemm_f16_tcgen05(x, w_nk, bias, y, m, n, k, ldy, act, out_f32, st);
     if (m > kSkinnyMaxM && gemm_tcgen05_supported(m, n, k, 2))
         return gemm_f16_tcgen05(x, w_nk, bias, y, m, n, k, ldy, act, out_f32, st);
-    return gemm_f16_skinny(x, w_nk, bias, y, m, n, k, ldy, act, out_f32, st);
+    return gemm_f16_skinny(x, w_nk, bias, y, m, n, k, ldy, act, out_f32, next, st);
+}
+
+extern "C" int ftcf_gemm_f16(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
+                             int out_f32, int impl, void* stream)
+{
+    return ftcf_gemm_f16_ex(x, w_nk, bias, y, m, n, k, ldy, act, out_f32, impl, nullptr, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ quantiser (CPU)

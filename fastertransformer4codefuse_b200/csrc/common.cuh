@@ -44,10 +44,39 @@ extern std::atomic<long long> g_launch_count;   // kernels launched by this libr
     } while (0)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Programmatic dependent launch (PDL): the decode step is a chain of short HBM-bound kernels; with this attribute the next
+// kernel's CTAs become resident while the previous kernel drains, run their independent prologue (L2 prefetch of their
+// weights / KV rows) and block in `griddepcontrol.wait` until the producer has completed.  Every kernel launched through
+// launch_pdl() calls pdl_wait() before it reads or writes anything another kernel touches.
+extern std::atomic<int> g_pdl_enabled;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl_enabled.load(std::memory_order_relaxed) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Ask L2 to fetch `bytes` (multiple of 16, 16-byte aligned address) -- no registers, no completion to wait for.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll

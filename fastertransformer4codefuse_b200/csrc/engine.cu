@@ -156,6 +156,8 @@ struct ftcf_gptneox {
     cudaStream_t stream = nullptr;          // the engine's own non-blocking stream: all work (and the captured graph) runs here
     cudaStream_t caller_stream = nullptr;   // the stream handed in at construction (torch's current stream, GptNeoXOp.h:180)
     cudaEvent_t caller_ev = nullptr;
+    cudaStream_t side = nullptr;            // second branch of the decode layer (FFN) so that it overlaps the attention branch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int h = 0, Hl = 0, hl = 0, inter_l = 0, Vp = 0, Vl = 0, t = 1, rank = 0;
     std::vector<LayerW> layers;
     const __half *wte = nullptr, *lnf_g = nullptr, *lnf_b = nullptr, *lm_head = nullptr;
@@ -163,10 +165,10 @@ struct ftcf_gptneox {
     ncclComm_t comm = nullptr;
 
     // options
-    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0;
+    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1;
 
     // request-sized buffers (grow only)
-    DevBuf kv, x, x2, n1, qkv, qbuf, ctx, attn, inter, ffn, logits, logits_local, logits_gather, samp_ws, small, mmha_part,
+    DevBuf kv, x, x2, n1, n2, qkv, qbuf, ctx, attn, inter, ffn, logits, logits_local, logits_gather, samp_ws, small, mmha_part,
         prompt_meta, lm_pad;
     int32_t* host_flag = nullptr;       // mapped pinned: [0] finished count, [1] step it belongs to
     int32_t* host_flag_dev = nullptr;
@@ -192,13 +194,12 @@ struct Small {   // carved out of one small device slab; all int32 / float / u8 
     void* curand;
 };
 
-int engine_gemm(ftcf_gptneox* e, const void* x, int layer, int kind, const __half* bias, void* y, int m, int n, int k, int act)
+int engine_gemm(ftcf_gptneox* e, cudaStream_t st, const void* x, int layer, int kind, const __half* bias, void* y, int m, int n, int k, int act)
 {
     const LayerW& L = e->layers[layer];
     if (e->cfg.int8_mode == 1)
-        return ftcf_gemm_w8a16(x, static_cast<const uint8_t*>(L.w[kind]), L.scale[kind], bias, y, m, n, k, act, e->opt_gemm_impl,
-                               e->stream);
-    return ftcf_gemm_f16(x, L.w[kind], bias, y, m, n, k, n, act, 0, e->opt_gemm_impl, e->stream);
+        return ftcf_gemm_w8a16(x, static_cast<const uint8_t*>(L.w[kind]), L.scale[kind], bias, y, m, n, k, act, e->opt_gemm_impl, st);
+    return ftcf_gemm_f16(x, L.w[kind], bias, y, m, n, k, n, act, 0, e->opt_gemm_impl, st);
 }
 
 int engine_allreduce(ftcf_gptneox* e, void* buf, size_t count)
@@ -223,23 +224,39 @@ int run_layer(ftcf_gptneox* e, int l, int m, AttnFn&& attn_fn)
     const ftcf_gptneox_config& c = e->cfg;
     cudaStream_t st = e->stream;
     __half* x = e->x.as<__half>();
-    FTCF_TRY(ftcf_layernorm(x, L.ln1_g, L.ln1_b, e->n1.p, m, e->h, c.layernorm_eps, st));
-    FTCF_TRY(engine_gemm(e, e->n1.p, l, 0, nullptr, e->qkv.p, m, 3 * e->hl, e->h, 0));
-    FTCF_TRY(attn_fn(l));
-    FTCF_TRY(engine_gemm(e, e->ctx.p, l, 1, nullptr, e->attn.p, m, e->h, e->hl, 0));
     if (c.use_gptj_residual) {
-        FTCF_TRY(ftcf_layernorm(x, L.ln2_g, L.ln2_b, e->n1.p, m, e->h, c.layernorm_eps, st));
-        FTCF_TRY(engine_gemm(e, e->n1.p, l, 2, L.ffn1_b, e->inter.p, m, e->inter_l, e->h, 1));
-        FTCF_TRY(engine_gemm(e, e->inter.p, l, 3, nullptr, e->ffn.p, m, e->h, e->inter_l, 0));
+        // Parallel residual: the attention branch (LN1, QKV, attention, O) and the FFN branch (LN2, FFN1, FFN2) only meet in
+        // the residual add (GptNeoXDecoder.cc:301-360).  At decode sizes every kernel is a short HBM-bound stream, so the two
+        // branches run on two streams (two parallel branches of the captured graph): one branch's kernel boundaries, LayerNorm
+        // and the latency-bound attention kernel are covered by the other branch's weight streaming.
+        const bool fork = e->opt_two_branch != 0 && m <= 32;
+        cudaStream_t sb = fork ? e->side : st;
+        if (fork) {
+            FTCF_CUDA_CHECK(cudaEventRecord(e->ev_fork, st));
+            FTCF_CUDA_CHECK(cudaStreamWaitEvent(sb, e->ev_fork, 0));
+        }
+        FTCF_TRY(ftcf_layernorm(x, L.ln2_g, L.ln2_b, e->n2.p, m, e->h, c.layernorm_eps, sb));
+        FTCF_TRY(engine_gemm(e, sb, e->n2.p, l, 2, L.ffn1_b, e->inter.p, m, e->inter_l, e->h, 1));
+        FTCF_TRY(engine_gemm(e, sb, e->inter.p, l, 3, nullptr, e->ffn.p, m, e->h, e->inter_l, 0));
+        if (fork) FTCF_CUDA_CHECK(cudaEventRecord(e->ev_join, sb));
+        FTCF_TRY(ftcf_layernorm(x, L.ln1_g, L.ln1_b, e->n1.p, m, e->h, c.layernorm_eps, st));
+        FTCF_TRY(engine_gemm(e, st, e->n1.p, l, 0, nullptr, e->qkv.p, m, 3 * e->hl, e->h, 0));
+        FTCF_TRY(attn_fn(l));
+        FTCF_TRY(engine_gemm(e, st, e->ctx.p, l, 1, nullptr, e->attn.p, m, e->h, e->hl, 0));
+        if (fork) FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join, 0));
         // ffn2_b slot holds the summed (o + ffn2) bias, already divided by t (huggingface_convert.py:35-41,192-206)
         FTCF_TRY(ftcf_add_bias_attn_ffn_residual(x, e->ffn.p, e->attn.p, x, L.ffn2_b, m, e->h, e->t, st));
         FTCF_TRY(engine_allreduce(e, x, (size_t)m * e->h));
     } else {
+        FTCF_TRY(ftcf_layernorm(x, L.ln1_g, L.ln1_b, e->n1.p, m, e->h, c.layernorm_eps, st));
+        FTCF_TRY(engine_gemm(e, st, e->n1.p, l, 0, nullptr, e->qkv.p, m, 3 * e->hl, e->h, 0));
+        FTCF_TRY(attn_fn(l));
+        FTCF_TRY(engine_gemm(e, st, e->ctx.p, l, 1, nullptr, e->attn.p, m, e->h, e->hl, 0));
         FTCF_TRY(engine_allreduce(e, e->attn.p, (size_t)m * e->h));
         // x2 = attn + bias_o + x ; n1 = LN2(x2)
         FTCF_TRY(ftcf_add_bias_residual_layernorm(x, e->attn.p, L.o_b, e->x2.p, L.ln2_g, L.ln2_b, e->n1.p, m, e->h, c.layernorm_eps, st));
-        FTCF_TRY(engine_gemm(e, e->n1.p, l, 2, L.ffn1_b, e->inter.p, m, e->inter_l, e->h, 1));
-        FTCF_TRY(engine_gemm(e, e->inter.p, l, 3, nullptr, e->ffn.p, m, e->h, e->inter_l, 0));
+        FTCF_TRY(engine_gemm(e, st, e->n1.p, l, 2, L.ffn1_b, e->inter.p, m, e->inter_l, e->h, 1));
+        FTCF_TRY(engine_gemm(e, st, e->inter.p, l, 3, nullptr, e->ffn.p, m, e->h, e->inter_l, 0));
         FTCF_TRY(engine_allreduce(e, e->ffn.p, (size_t)m * e->h));
         FTCF_TRY(ftcf_add_bias_residual(x, e->ffn.p, e->x2.p, L.ffn2_b, m, e->h, st));
     }
@@ -285,7 +302,10 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
     // Stream capture is not allowed on the legacy default stream, which is what torch hands over by default, so the
     // engine owns a stream and orders it after the caller's with an event at the start of every request.
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->caller_ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&e->caller_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         set_error("create: cannot create the engine stream");
         delete e;
         return FTCF_ERR_CUDA;
@@ -386,13 +406,16 @@ extern "C" void ftcf_gptneox_destroy(ftcf_gptneox* e)
     if (!e) return;
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     for (auto& b : e->owned) b.release();
-    DevBuf* bufs[] = {&e->kv, &e->x, &e->x2, &e->n1, &e->qkv, &e->qbuf, &e->ctx, &e->attn, &e->inter, &e->ffn, &e->logits,
+    DevBuf* bufs[] = {&e->kv, &e->x, &e->x2, &e->n1, &e->n2, &e->qkv, &e->qbuf, &e->ctx, &e->attn, &e->inter, &e->ffn, &e->logits,
                       &e->logits_local, &e->logits_gather, &e->samp_ws, &e->small, &e->mmha_part, &e->prompt_meta, &e->lm_pad};
     for (DevBuf* b : bufs) b->release();
     if (e->host_flag) cudaFreeHost(e->host_flag);
     if (e->host_stage) cudaFreeHost(e->host_stage);
     if (e->comm && g_nccl.ok) g_nccl.CommDestroy(e->comm);
     if (e->caller_ev) cudaEventDestroy(e->caller_ev);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->side) cudaStreamDestroy(e->side);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -404,6 +427,7 @@ extern "C" int ftcf_gptneox_set_option(ftcf_gptneox* e, const char* name, int va
     if (n == "cuda_graph") e->opt_cuda_graph = value;
     else if (n == "gemm_impl") e->opt_gemm_impl = value;
     else if (n == "step_timing") e->opt_step_timing = value;
+    else if (n == "two_branch") e->opt_two_branch = value;
     else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_option: unknown option %s", name);
     if (e->graph_exec) {   // anything captured may be stale
         cudaGraphExecDestroy(e->graph_exec);
@@ -541,6 +565,7 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     FTCF_TRY(e->x.ensure((size_t)m_max * e->h * 2));
     FTCF_TRY(e->x2.ensure((size_t)m_max * e->h * 2));
     FTCF_TRY(e->n1.ensure((size_t)m_max * e->h * 2));
+    FTCF_TRY(e->n2.ensure((size_t)m_max * e->h * 2));
     FTCF_TRY(e->qkv.ensure((size_t)m_max * 3 * e->hl * 2));
     FTCF_TRY(e->qbuf.ensure((size_t)m_max * e->hl * 2));
     FTCF_TRY(e->ctx.ensure((size_t)m_max * e->hl * 2));

@@ -15,7 +15,7 @@
 //     fragments come from ONE contiguous 16-byte piece of a weight row (no shuffles, no transposes);
 //   * cross-warp (split-k inside the CTA) reduction through shared memory in a fixed order -> deterministic;
 //   * epilogue: per-column scale (fp32), bias, tanh-GELU, fp16 (or fp32 logits) store.
-#include "common.cuh"
+#include "tma_utils.cuh"
 
 namespace ftcf {
 
@@ -45,172 +45,270 @@ __device__ __forceinline__ uint32_t u4_get(const uint4& v, int i)
     return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
 }
 
-template <typename WT, int RT, int MT, int EPI>
-__global__ void __launch_bounds__(256)
-gemm_skinny_kernel(const __half* __restrict__ x, const WT* __restrict__ w, const __half* __restrict__ scale,
-                   const __half* __restrict__ bias, void* __restrict__ y, int m, int n, int k, int ldy, int act)
+// tunables (ftcf_set_tunable): how many CTAs one launch aims for (all of them co-resident, so HBM is shared evenly and the
+// next kernel's CTAs fit beside them) -- see launch_skinny.
+std::atomic<int> g_sk_target_ctas{296};
+std::atomic<int> g_sk_prefetch_rows{0};  // rows of each NEXT-kernel CTA slice that a finishing CTA prefetches into L2; measured on B200: it does not pay (gcb_2.log), so 0 = off
+
+namespace sk {
+constexpr int ROWS = 32;                 // output features per pass (two 16-row MMA tiles)
+constexpr int CHUNK = 512;               // bytes of one weight row per stage (4 k-steps of 128 bytes)
+constexpr int SUB_BYTES = ROWS * 128;    // one TMA box: 32 rows x 128 bytes, SWIZZLE_128B
+constexpr int STAGE_BYTES = 4 * SUB_BYTES;
+constexpr int STAGES = 4;
+constexpr int THREADS = 288;             // warp 0: TMA producer, warps 1..8: consumers
+using namespace tma;
+}  // namespace sk
+
+// Pipelined skinny GEMM.  One CTA owns the contiguous feature rows [r0, r1) and all of k.
+//   producer      : one thread issues four TMA boxes (32 rows x 128 bytes, SWIZZLE_128B) per stage, 4 stages = 64 KB in flight
+//                   per CTA and no registers; it never waits for the producer KERNEL (weights are constants), so with PDL
+//                   the ring is already full when the previous kernel retires;
+//   consumer warps: warp (tile r, k-step ks) reads its 16 x 128-byte fragment (4 LDS.128 per lane, conflict-free through the
+//                   128-byte swizzle), converts
+//                   u8 -> fp16 in registers and issues mma.sync.m16n8k16 against the token fragments (read through L1);
+//   end of a pass : the four k-step warps of a tile are summed through shared memory in a fixed order, epilogue, store.
+template <typename WT, int MT, int EPI>
+__global__ void __launch_bounds__(sk::THREADS, (MT <= 2 ? 2 : 1))
+gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __half* __restrict__ x, const __half* __restrict__ scale,
+                   const __half* __restrict__ bias, void* __restrict__ y, int m, int n, int k, int ldy, int act, int rows_per_cta,
+                   const uint8_t* __restrict__ next_w, int next_n, int next_row_bytes, int next_rows_per_cta, int next_pf_rows)
 {
+    using namespace sk;
     constexpr int EPC = 16 / sizeof(WT);   // k-elements per 16-byte chunk
-    constexpr int KSTEP = 8 * EPC;         // k-elements a warp consumes per step (4 lanes x 2 chunks)
-    constexpr int NMMA = EPC / 4;          // mma per chunk
-    constexpr int XV = EPC / 4;            // uint4 per lane per token per step (2*EPC halves)
-    constexpr int NF = 16 * RT, NT = 8 * MT, PITCH = NF + 4;
+    constexpr int KSTEP = 8 * EPC;         // k-elements per 128-byte k-step
+    constexpr int NMMA = EPC / 4;          // mma per 16-byte chunk
+    constexpr int XV = EPC / 4;            // uint4 per lane per token group per k-step
+    constexpr int NT = 8 * MT;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int n0 = blockIdx.x * NF, m0 = blockIdx.y * NT;
+    extern __shared__ __align__(1024) uint8_t sk_smem_raw[];
+    uint8_t* sk_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sk_smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES];
+    __shared__ float red[8][NT][16 + 4];
 
-    float acc[RT][MT][4];
-#pragma unroll
-    for (int r = 0; r < RT; ++r)
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[r][mt][i] = 0.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(n, r0 + rows_per_cta);
+    const int m0 = blockIdx.y * NT;
+    const int row_bytes = k * (int)sizeof(WT);
+    const int chunks = (row_bytes + CHUNK - 1) / CHUNK;
+    const int passes = (r1 - r0 + ROWS - 1) / ROWS;
+    const int total = passes * chunks;       // stages this CTA streams
 
-    const WT* wrow[RT][2];
-#pragma unroll
-    for (int r = 0; r < RT; ++r)
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const int row = min(n0 + r * 16 + g + 8 * hh, n - 1);
-            wrow[r][hh] = w + (size_t)row * k + t * 2 * EPC;
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 8);
         }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ================= producer =================
+        if (lane == 0) {
+            prefetch_map(&map_w);
+            for (int i = 0; i < total; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                const int pass = i / chunks, kc = i % chunks;
+                const int nsub = min(4, (row_bytes - kc * CHUNK) / 128);     // 128-byte k-steps in this chunk
+                mbar_wait(&bar_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&bar_full[s], (uint32_t)(nsub * SUB_BYTES));
+                for (int j = 0; j < nsub; ++j)
+                    load_2d(sk_smem + (size_t)s * STAGE_BYTES + j * SUB_BYTES, &map_w, &bar_full[s],
+                            (kc * CHUNK + j * 128) / (int)sizeof(WT), r0 + pass * ROWS);
+            }
+        }
+        // Tail prefetch: everything this CTA needs has been requested; queue L2 prefetches for the HEAD of the next GEMM's
+        // weight stream (the first rows of the slices its CTAs will own) behind them, so HBM keeps working through this
+        // kernel's drain, the launch gap and the next kernel's ramp-up instead of idling (~8 us per boundary otherwise).
+        if (next_w != nullptr && blockIdx.y == 0) {
+            __syncwarp();
+            const int next_ctas = (next_n + next_rows_per_cta - 1) / next_rows_per_cta;
+            for (int c = blockIdx.x; c < next_ctas; c += gridDim.x) {
+                const int nr0 = c * next_rows_per_cta, nr1 = min(next_n, nr0 + min(next_rows_per_cta, next_pf_rows));
+                for (int row = nr0 + lane; row < nr1; row += 32)
+                    l2_prefetch_bulk(next_w + (size_t)row * next_row_bytes, (uint32_t)next_row_bytes);
+            }
+        }
+        return;
+    }
+
+    // ================= consumers =================
+    const int cw = warp - 1, tile = cw >> 2, ks = cw & 3;
+    const int g = lane >> 2, t = lane & 3;
+    pdl_wait();                              // x comes from the previous kernel; y may still be read by it
     const __half* xrow[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         const int tok = min(m0 + mt * 8 + g, m - 1);
-        xrow[mt] = x + (size_t)tok * k + t * 2 * EPC;
+        xrow[mt] = x + (size_t)tok * k + ks * KSTEP + t * 2 * EPC;
     }
-
-    const int iters = k / KSTEP;
-#pragma unroll 2
-    for (int it = warp; it < iters; it += 8) {
-        const int kb = it * KSTEP;
-        uint4 wv[RT][2][2];
-#pragma unroll
-        for (int r = 0; r < RT; ++r)
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) wv[r][hh][c] = ld_stream_16(wrow[r][hh] + kb + c * EPC);
-        uint4 xv[MT][XV];
+    int i = 0;
+    for (int pass = 0; pass < passes; ++pass) {
+        float acc[MT][4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int i = 0; i < XV; ++i) xv[mt][i] = ld_ro_16(xrow[mt] + kb + i * 8);
-
+            for (int j = 0; j < 4; ++j) acc[mt][j] = 0.f;
+        for (int kc = 0; kc < chunks; ++kc, ++i) {
+            const int s = i % STAGES;
+            const uint32_t ph = (i / STAGES) & 1;
+            const bool active = (kc * CHUNK + ks * 128) < row_bytes;     // last chunk of a row may be short
+            uint4 xv[MT][XV];
+            if (active) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+                for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int j = 0; j < NMMA; ++j) {
-                const int pi = c * (EPC / 2) + 2 * j;   // 32-bit word index into the lane's x block
-                uint32_t a[RT][4];
-#pragma unroll
-                for (int r = 0; r < RT; ++r) {
-                    if constexpr (sizeof(WT) == 1) {
-                        u8x4_to_h2x2(u4_get(wv[r][0][c], j), a[r][0], a[r][2]);
-                        u8x4_to_h2x2(u4_get(wv[r][1][c], j), a[r][1], a[r][3]);
-                    } else {
-                        a[r][0] = u4_get(wv[r][0][c], 2 * j);
-                        a[r][2] = u4_get(wv[r][0][c], 2 * j + 1);
-                        a[r][1] = u4_get(wv[r][1][c], 2 * j);
-                        a[r][3] = u4_get(wv[r][1][c], 2 * j + 1);
-                    }
-                }
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const uint32_t b0 = u4_get(xv[mt][pi / 4], pi % 4);
-                    const uint32_t b1 = u4_get(xv[mt][(pi + 1) / 4], (pi + 1) % 4);
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) mma_16816(acc[r][mt], a[r][0], a[r][1], a[r][2], a[r][3], b0, b1);
-                }
+                    for (int q = 0; q < XV; ++q) xv[mt][q] = ld_ro_16(xrow[mt] + (size_t)kc * (CHUNK / (int)sizeof(WT)) + q * 8);
             }
-    }
-
-    // ---- reduce the 8 warps' partial sums (fixed order), epilogue, store
-    __shared__ float red[8][NT][PITCH];
+            mbar_wait(&bar_full[s], ph);
+            if (active) {
+                // box layout: row r at r * 128 bytes, 16-byte chunk c stored at chunk (c ^ (r & 7))  (SWIZZLE_128B)
+                const int rl = tile * 16 + g;                      // rl & 7 == (rl + 8) & 7 == g & 7
+                const uint8_t* st = sk_smem + (size_t)s * STAGE_BYTES + ks * SUB_BYTES + rl * 128;
+                uint4 wv[2][2];
 #pragma unroll
-    for (int r = 0; r < RT; ++r)
+                for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        wv[hh][c] = *reinterpret_cast<const uint4*>(st + hh * 8 * 128 + (((2 * t + c) ^ (g & 7)) << 4));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[s]);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int j = 0; j < NMMA; ++j) {
+                        const int pi = c * (EPC / 2) + 2 * j;
+                        uint32_t a0, a1, a2, a3;
+                        if constexpr (sizeof(WT) == 1) {
+                            u8x4_to_h2x2(u4_get(wv[0][c], j), a0, a2);
+                            u8x4_to_h2x2(u4_get(wv[1][c], j), a1, a3);
+                        } else {
+                            a0 = u4_get(wv[0][c], 2 * j);
+                            a2 = u4_get(wv[0][c], 2 * j + 1);
+                            a1 = u4_get(wv[1][c], 2 * j);
+                            a3 = u4_get(wv[1][c], 2 * j + 1);
+                        }
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt)
+                            mma_16816(acc[mt], a0, a1, a2, a3, u4_get(xv[mt][pi / 4], pi % 4), u4_get(xv[mt][(pi + 1) / 4], (pi + 1) % 4));
+                    }
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[s]);
+            }
+        }
+        // ---- sum the four k-step warps of each tile (fixed order), epilogue, store
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-            const int f = r * 16 + g, tok = mt * 8 + 2 * t;
-            red[warp][tok][f] = acc[r][mt][0];
-            red[warp][tok + 1][f] = acc[r][mt][1];
-            red[warp][tok][f + 8] = acc[r][mt][2];
-            red[warp][tok + 1][f + 8] = acc[r][mt][3];
+            const int tok = mt * 8 + 2 * t;
+            red[cw][tok][g] = acc[mt][0];
+            red[cw][tok + 1][g] = acc[mt][1];
+            red[cw][tok][g + 8] = acc[mt][2];
+            red[cw][tok + 1][g + 8] = acc[mt][3];
         }
-    __syncthreads();
-    for (int o = threadIdx.x; o < NF * NT; o += 256) {
-        const int f = o % NF, tok = o / NF;
-        const int col = n0 + f, row = m0 + tok;
-        if (col >= n || row >= m) continue;
-        float v = 0.f;
-#pragma unroll
-        for (int wi = 0; wi < 8; ++wi) v += red[wi][tok][f];
-        if constexpr (EPI == EPI_W8) {
-            v *= __half2float(scale[col]);
-            if (bias != nullptr) v += __half2float(bias[col]);
-            if (act == 1) v = gelu_tanh_f32(v);
-            reinterpret_cast<__half*>(y)[(size_t)row * ldy + col] = __float2half_rn(v);
-        } else if constexpr (EPI == EPI_F16) {
-            __half hv = __float2half_rn(v);
-            if (bias != nullptr) hv = __hadd(hv, bias[col]);
-            if (act == 1) hv = gelu_tanh_half_ref(hv);
-            reinterpret_cast<__half*>(y)[(size_t)row * ldy + col] = hv;
-        } else {
-            reinterpret_cast<float*>(y)[(size_t)row * ldy + col] = v;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int p0 = r0 + pass * ROWS;
+        for (int o = threadIdx.x - 32; o < ROWS * NT; o += 256) {
+            const int f = o % ROWS, tok = o / ROWS;
+            const int col = p0 + f, row = m0 + tok;
+            if (col >= r1 || row >= m) continue;
+            const int tl = f >> 4, fl = f & 15;
+            float v = red[tl * 4 + 0][tok][fl] + red[tl * 4 + 1][tok][fl];
+            v += red[tl * 4 + 2][tok][fl];
+            v += red[tl * 4 + 3][tok][fl];
+            if constexpr (EPI == EPI_W8) {
+                v *= __half2float(scale[col]);
+                if (bias != nullptr) v += __half2float(bias[col]);
+                if (act == 1) v = gelu_tanh_f32(v);
+                reinterpret_cast<__half*>(y)[(size_t)row * ldy + col] = __float2half_rn(v);
+            } else if constexpr (EPI == EPI_F16) {
+                __half hv = __float2half_rn(v);
+                if (bias != nullptr) hv = __hadd(hv, bias[col]);
+                if (act == 1) hv = gelu_tanh_half_ref(hv);
+                reinterpret_cast<__half*>(y)[(size_t)row * ldy + col] = hv;
+            } else {
+                reinterpret_cast<float*>(y)[(size_t)row * ldy + col] = v;
+            }
         }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+}
+
+static int skinny_rows_per_cta(int n)
+{
+    // every CTA gets the same whole number of 32-row passes; all CTAs of the launch are co-resident (<= target), so the
+    // weight stream is shared evenly by HBM even when the CTA count is not a multiple of the SM count
+    const int tiles = ceil_div(n, sk::ROWS);
+    const int passes = ceil_div(tiles, g_sk_target_ctas.load(std::memory_order_relaxed));
+    return passes * sk::ROWS;
 }
 
 template <typename WT, int EPI>
 static int launch_skinny(const void* x, const void* w, const void* scale, const void* bias, void* y, int m, int n, int k,
-                         int ldy, int act, cudaStream_t st)
+                         int ldy, int act, const ftcf_prefetch_hint* next, cudaStream_t st)
 {
     constexpr int EPC = 16 / sizeof(WT);
     FTCF_REQUIRE(k % (8 * EPC) == 0, FTCF_ERR_UNSUPPORTED, "skinny gemm: k=%d must be a multiple of %d", k, 8 * EPC);
     FTCF_REQUIRE(m > 0 && n > 0, FTCF_ERR_INVALID, "skinny gemm: empty problem m=%d n=%d", m, n);
     const int mt = m >= 25 ? 4 : ceil_div(m, 8);
-    const bool wide = n >= 16 * 2 * 148 * 2;
-    const dim3 block(256);
+    const int rows_per_cta = skinny_rows_per_cta(n);
+    const uint8_t* next_w = nullptr;
+    int next_n = 0, next_row_bytes = 0, next_rpc = 1;
+    const int next_pf = g_sk_prefetch_rows.load(std::memory_order_relaxed);
+    if (next != nullptr && next->w != nullptr && next_pf > 0 && next->row_bytes % 16 == 0) {
+        next_w = static_cast<const uint8_t*>(next->w);
+        next_n = next->n;
+        next_row_bytes = next->row_bytes;
+        next_rpc = skinny_rows_per_cta(next->n);
+    }
+    const dim3 grid(ceil_div(n, rows_per_cta), ceil_div(m, 8 * mt));
+    const dim3 block(sk::THREADS);
+    const size_t smem = (size_t)sk::STAGES * sk::STAGE_BYTES + 1024;
     const __half* xs = static_cast<const __half*>(x);
-    const WT* ws = static_cast<const WT*>(w);
+    CUtensorMap mw;
+    {
+        const int rc = make_tensor_map_2d(&mw, w, n, k, (int)sizeof(WT), sk::ROWS);
+        if (rc != FTCF_OK) return rc;
+    }
     const __half* sc = static_cast<const __half*>(scale);
     const __half* bs = static_cast<const __half*>(bias);
-#define FTCF_SK(RT_, MT_)                                                                                      \
-    gemm_skinny_kernel<WT, RT_, MT_, EPI><<<dim3(ceil_div(n, 16 * RT_), ceil_div(m, 8 * MT_)), block, 0, st>>>( \
-        xs, ws, sc, bs, y, m, n, k, ldy, act)
-    if (wide) {
-        switch (mt) {
-            case 1: FTCF_SK(2, 1); break;
-            case 2: FTCF_SK(2, 2); break;
-            case 3: FTCF_SK(2, 3); break;
-            default: FTCF_SK(2, 4); break;
-        }
-    } else {
-        switch (mt) {
-            case 1: FTCF_SK(1, 1); break;
-            case 2: FTCF_SK(1, 2); break;
-            case 3: FTCF_SK(1, 3); break;
-            default: FTCF_SK(1, 4); break;
-        }
+    cudaError_t err = cudaSuccess;
+#define FTCF_SK(MT_)                                                                                                    \
+    do {                                                                                                                \
+        static bool configured = false;                                                                                 \
+        if (!configured) {                                                                                              \
+            err = cudaFuncSetAttribute(gemm_skinny_kernel<WT, MT_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            configured = true;                                                                                          \
+        }                                                                                                               \
+        if (err == cudaSuccess)                                                                                         \
+            err = launch_pdl(gemm_skinny_kernel<WT, MT_, EPI>, grid, block, smem, st, mw, xs, sc, bs, y, m, n, k, ldy, act, rows_per_cta, next_w, next_n, next_row_bytes, next_rpc, next_pf); \
+    } while (0)
+    switch (mt) {
+        case 1: FTCF_SK(1); break;
+        case 2: FTCF_SK(2); break;
+        case 3: FTCF_SK(3); break;
+        default: FTCF_SK(4); break;
     }
 #undef FTCF_SK
+    FTCF_REQUIRE(err == cudaSuccess, FTCF_ERR_CUDA, "skinny gemm launch failed: %s", cudaGetErrorString(err));
     FTCF_LAUNCH_CHECK();
     return FTCF_OK;
 }
 
 int gemm_w8a16_skinny(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n, int k,
-                      int act, cudaStream_t st)
+                      int act, const ftcf_prefetch_hint* next, cudaStream_t st)
 {
-    return launch_skinny<uint8_t, EPI_W8>(x, w_nk, scale, bias, y, m, n, k, n, act, st);
+    return launch_skinny<uint8_t, EPI_W8>(x, w_nk, scale, bias, y, m, n, k, n, act, next, st);
 }
 
 int gemm_f16_skinny(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
-                    int out_f32, cudaStream_t st)
+                    int out_f32, const ftcf_prefetch_hint* next, cudaStream_t st)
 {
-    if (out_f32) return launch_skinny<__half, EPI_F32>(x, w_nk, nullptr, bias, y, m, n, k, ldy, act, st);
-    return launch_skinny<__half, EPI_F16>(x, w_nk, nullptr, bias, y, m, n, k, ldy, act, st);
+    if (out_f32) return launch_skinny<__half, EPI_F32>(x, w_nk, nullptr, bias, y, m, n, k, ldy, act, next, st);
+    return launch_skinny<__half, EPI_F16>(x, w_nk, nullptr, bias, y, m, n, k, ldy, act, next, st);
 }
 
 // ---------------------------------------------------------------- fp16 [k,n] -> [n,k]

@@ -17,9 +17,7 @@
 //     releases the shared-memory stage and the TMEM A-stage back to their producers.
 //   * epilogue: tcgen05.ld of the accumulator rows, per-feature dequant scale (fp32), bias, tanh-GELU, fp16/fp32 store.
 //   * fp16 weights (int8_mode = 0, LM head): same pipeline, A comes from shared memory through a UMMA descriptor.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tma_utils.cuh"
 
 namespace ftcf {
 
@@ -30,45 +28,12 @@ constexpr int kConvWarps = 8;
 constexpr int kTileM = 128;            // output features per CTA (UMMA M)
 constexpr int kAStages = 4;            // TMEM A-operand stages (u8 path), 64 columns each
 constexpr uint32_t kTmemCols = 512;
-constexpr long long kSpinLimit = 1ll << 22;   // bounded waits: a pipeline bug traps instead of hanging the GPU
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    for (long long spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (spin > kSpinLimit) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
+using tma::smem_u32;
+using tma::mbar_init;
+using tma::mbar_arrive;
+using tma::mbar_arrive_expect_tx;
+using tma::mbar_wait;
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) { tma::load_2d(smem_dst, map, bar, c0, c1); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar)
@@ -328,39 +293,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (fn) return fn;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
-        return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-    return fn;
-}
-
-// 2-D row-major [rows, cols] tensor of `elem` bytes, box = [box_rows, 128 bytes], SWIZZLE_128B, zero fill out of bounds
-static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int elem, int box_rows)
-{
-    EncodeTiledFn enc = get_encode();
-    FTCF_REQUIRE(enc != nullptr, FTCF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)cols * elem};
-    const cuuint32_t box[2] = {(cuuint32_t)(128 / elem), (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(map, elem == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base),
-                           dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    FTCF_REQUIRE(r == CUDA_SUCCESS, FTCF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a [%d x %d] tensor of %d-byte elements", (int)r,
-                 rows, cols, elem);
-    return FTCF_OK;
-}
-
 template <bool W8, int NT, int STAGES, int EPI>
 static int launch(const CUtensorMap& mw, const CUtensorMap& mx, const Args& a, cudaStream_t st)
 {
@@ -384,9 +316,9 @@ static int dispatch(const void* x, const void* w, const Args& a, cudaStream_t st
     constexpr int elem = W8 ? 1 : 2;
     CUtensorMap mw, mx;
     const int nt = a.m <= 16 ? 16 : (a.m <= 32 ? 32 : (a.m <= 64 ? 64 : 128));
-    int rc = make_map(&mw, w, a.n, a.k, elem, kTileM);
+    int rc = make_tensor_map_2d(&mw, w, a.n, a.k, elem, kTileM);
     if (rc != FTCF_OK) return rc;
-    rc = make_map(&mx, x, a.m, a.k, 2, nt);
+    rc = make_tensor_map_2d(&mx, x, a.m, a.k, 2, nt);
     if (rc != FTCF_OK) return rc;
     switch (nt) {
         case 16: return launch<W8, 16, 8, EPI>(mw, mx, a, st);
@@ -397,6 +329,40 @@ static int dispatch(const void* x, const void* w, const Args& a, cudaStream_t st
 }
 
 }  // namespace tc
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// 2-D row-major [rows, cols] tensor of `elem` bytes, box = [box_rows, 128 bytes], SWIZZLE_128B, zero fill out of bounds
+int make_tensor_map_2d(CUtensorMap* map, const void* base, int rows, int cols, int elem, int box_rows)
+{
+    EncodeTiledFn enc = get_encode();
+    FTCF_REQUIRE(enc != nullptr, FTCF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * elem};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / elem), (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, elem == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base),
+                           dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FTCF_REQUIRE(r == CUDA_SUCCESS, FTCF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a [%d x %d] tensor of %d-byte elements", (int)r,
+                 rows, cols, elem);
+    return FTCF_OK;
+}
+
 
 bool gemm_tcgen05_supported(int m, int n, int k, int elem_bytes)
 {

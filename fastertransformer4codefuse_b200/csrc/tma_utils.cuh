@@ -1,0 +1,59 @@
+// mbarrier / TMA helpers shared by the tcgen05 GEMM and the skinny streaming GEMM.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ftcf {
+
+// 2-D row-major [rows, cols] tensor of `elem`-byte elements; box = [box_rows, 128 bytes]; SWIZZLE_128B; out-of-bounds
+// elements read as zero.  Host side, defined in gemm_tcgen05.cu (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint).
+int make_tensor_map_2d(CUtensorMap* map, const void* base, int rows, int cols, int elem, int box_rows);
+
+#ifdef __CUDACC__
+namespace tma {
+constexpr long long kSpinLimit = 1ll << 22;   // bounded waits: a pipeline bug traps instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (long long spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (spin > kSpinLimit) __trap();
+    }
+}
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
+// one box of the tensor map -> shared memory; c0 = element column, c1 = row
+__device__ __forceinline__ void load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+}  // namespace tma
+#endif
+
+}  // namespace ftcf

@@ -59,6 +59,11 @@ class GptNeoXOp:
         self._h = handle
         self._lib = lib
         self.last_stats = None
+        # experiment hook: FTCF_OPTIONS="two_branch=0,cuda_graph=1"
+        import os
+        for item in filter(None, os.environ.get("FTCF_OPTIONS", "").split(",")):
+            key, _, val = item.partition("=")
+            self.set_option(key.strip(), int(val))
 
     @staticmethod
     def _exchange_nccl_id(lib, comm, rank):

@@ -42,6 +42,9 @@ int ftcf_abi_version(void);
 int ftcf_device_check(void);
 /* Kernels (and NCCL collectives) launched by this library in this process so far. */
 long long ftcf_launch_count(void);
+/* Process-wide tuning knobs (defaults are the tuned values): "pdl" 0/1 programmatic dependent launch,
+ * "skinny_target_ctas" CTAs per skinny-GEMM launch, "skinny_prefetch_rows" rows each CTA prefetches into L2 up front. */
+int ftcf_set_tunable(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * Weight-only INT8 quantiser (CPU).  Replaces ft::symmetric_quantize<half,half|float> +
@@ -72,6 +75,15 @@ int ftcf_int8_ampere_to_b200_host(const int8_t* processed_ampere, size_t k, size
  * impl: 0 = auto, 1 = force the skinny (m <= 32 streaming) kernel, 2 = force the tcgen05 kernel. */
 int ftcf_gemm_w8a16(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n,
                     int k, int act, int impl, void* stream);
+/* Same, with a hint naming the weight matrix the NEXT GEMM on this stream will read (K-major, n rows of row_bytes):
+ * the streaming kernel queues L2 prefetches for the head of that matrix behind its own last loads, so HBM does not
+ * idle across the kernel boundary.  The hint is optional (NULL) and never changes results. */
+typedef struct {
+    const void* w;
+    int32_t n, row_bytes;
+} ftcf_prefetch_hint;
+int ftcf_gemm_w8a16_ex(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n,
+                       int k, int act, int impl, const ftcf_prefetch_hint* next, void* stream);
 
 /* y[m,n] = x[m,k] . W, W given K-major as W^T fp16 [n,k]; fp32 accumulate.  out_f32 = 1 writes fp32 (LM head
  * logits, models/gptneox/GptNeoX.cc:869-912), else fp16 with optional bias + tanh-GELU applied with the
@@ -79,6 +91,8 @@ int ftcf_gemm_w8a16(const void* x, const uint8_t* w_nk, const void* scale, const
  * ldy = row pitch of y in elements.  Replaces cublasMMWrapper::Gemm, utils/cublasMMWrapper.cc:154-328. */
 int ftcf_gemm_f16(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
                   int out_f32, int impl, void* stream);
+int ftcf_gemm_f16_ex(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
+                     int out_f32, int impl, const ftcf_prefetch_hint* next, void* stream);
 
 /* out[k,n] -> out_t[n,k] fp16 transpose (load-time re-layout of fp16 weights to K-major). */
 int ftcf_transpose_f16(const void* in_kn, void* out_nk, int k, int n, void* stream);
