@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "decode_mega.cuh"
 
 namespace ftcf {
 
@@ -165,11 +166,13 @@ struct ftcf_gptneox {
     ncclComm_t comm = nullptr;
 
     // options
-    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1;
+    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_mega = 1;
 
     // request-sized buffers (grow only)
     DevBuf kv, x, x2, n1, n2, qkv, qbuf, ctx, attn, inter, ffn, logits, logits_local, logits_gather, samp_ws, small, mmha_part,
-        prompt_meta, lm_pad;
+        prompt_meta, lm_pad, layer_dev, ffn_part, att_part, gbar;
+    mg::Params mega{};                  // persistent decode-step kernel arguments of the current request
+    bool mega_on = false;
     int32_t* host_flag = nullptr;       // mapped pinned: [0] finished count, [1] step it belongs to
     int32_t* host_flag_dev = nullptr;
     int32_t* host_stage = nullptr;      // pinned staging for small uploads / callback reads
@@ -375,6 +378,25 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
             e->lm_head = e->lm_pad.as<__half>();
         }
     }
+    if (status == FTCF_OK) {
+        // per-layer pointer table of the persistent decode-step kernel
+        std::vector<mg::LayerDev> ld(L);
+        for (int l = 0; l < L; ++l) {
+            const LayerW& lw = e->layers[l];
+            for (int kind = 0; kind < 4; ++kind) {
+                ld[l].w[kind] = lw.w[kind];
+                ld[l].scale[kind] = lw.scale[kind];
+            }
+            ld[l].ln1_g = lw.ln1_g; ld[l].ln1_b = lw.ln1_b; ld[l].ln2_g = lw.ln2_g; ld[l].ln2_b = lw.ln2_b;
+            ld[l].qkv_b = lw.qkv_b; ld[l].ffn1_b = lw.ffn1_b; ld[l].res_b = lw.ffn2_b;
+        }
+        status = e->layer_dev.ensure(sizeof(mg::LayerDev) * L);
+        if (status == FTCF_OK && cudaMemcpy(e->layer_dev.p, ld.data(), sizeof(mg::LayerDev) * L, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("create: upload of the layer table failed");
+            status = FTCF_ERR_CUDA;
+        }
+        if (status == FTCF_OK) status = e->gbar.ensure(256);
+    }
     if (status == FTCF_OK && t > 1) {
         if (!nccl_unique_id) { set_error("create: tensor_para_size %d needs an NCCL unique id", t); status = FTCF_ERR_INVALID; }
         if (status == FTCF_OK) status = nccl_load();
@@ -407,7 +429,8 @@ extern "C" void ftcf_gptneox_destroy(ftcf_gptneox* e)
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     for (auto& b : e->owned) b.release();
     DevBuf* bufs[] = {&e->kv, &e->x, &e->x2, &e->n1, &e->n2, &e->qkv, &e->qbuf, &e->ctx, &e->attn, &e->inter, &e->ffn, &e->logits,
-                      &e->logits_local, &e->logits_gather, &e->samp_ws, &e->small, &e->mmha_part, &e->prompt_meta, &e->lm_pad};
+                      &e->logits_local, &e->logits_gather, &e->samp_ws, &e->small, &e->mmha_part, &e->prompt_meta, &e->lm_pad, &e->layer_dev,
+                      &e->ffn_part, &e->att_part, &e->gbar};
     for (DevBuf* b : bufs) b->release();
     if (e->host_flag) cudaFreeHost(e->host_flag);
     if (e->host_stage) cudaFreeHost(e->host_stage);
@@ -428,6 +451,7 @@ extern "C" int ftcf_gptneox_set_option(ftcf_gptneox* e, const char* name, int va
     else if (n == "gemm_impl") e->opt_gemm_impl = value;
     else if (n == "step_timing") e->opt_step_timing = value;
     else if (n == "two_branch") e->opt_two_branch = value;
+    else if (n == "mega") e->opt_mega = value;
     else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_option: unknown option %s", name);
     if (e->graph_exec) {   // anything captured may be stale
         cudaGraphExecDestroy(e->graph_exec);
@@ -460,6 +484,16 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
     const ftcf_gptneox_config& c = e->cfg;
     cudaStream_t st = e->stream;
     const int dh = c.size_per_head;
+    if (e->mega_on) {
+        // one persistent kernel: embedding, L layers, final LayerNorm, LM head (decode_mega.cu)
+        mg::Params mp = e->mega;
+        mp.l0 = 0;
+        mp.l1 = run_layers ? c.layer_num : 0;
+        mp.embed = run_layers ? 1 : 0;
+        mp.out_ids = s.out_ids; mp.step = s.step; mp.seq_len = s.seq_len; mp.input_len = s.input_len; mp.pad_count = s.pad_count;
+        mp.finished = s.finished; mp.att_cnt = s.counters;
+        return mega_launch(mp, c.int8_mode == 1, st);
+    }
     if (run_layers) {
         const size_t total = (size_t)B * e->h / 8;
         embedding_prev_token_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->x.as<__half>(), e->wte, s.out_ids, s.step, B, e->h,
@@ -581,6 +615,29 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     FTCF_TRY(e->samp_ws.ensure(ws_bytes));
     const int splits = ftcf_mmha_choose_splits(B, e->Hl, max_len);
     FTCF_TRY(e->mmha_part.ensure((size_t)B * e->Hl * splits * (dh + 2) * 4 + 256));
+    e->mega_on = e->opt_mega != 0 &&
+                 mega_supported(B, e->h, e->hl, e->inter_l, dh, c.rotary_embedding_dim, c.int8_mode == 1, e->t, c.use_gptj_residual != 0);
+    if (e->mega_on) {
+        mg::Params& mp = e->mega;
+        mp = mg::Params{};
+        mp.layers = e->layer_dev.as<mg::LayerDev>();
+        mp.lm_rows = e->Vp;
+        mp.B = B; mp.h = e->h; mp.Hl = e->Hl; mp.hl = e->hl; mp.inter = e->inter_l; mp.dh = dh; mp.rot = c.rotary_embedding_dim;
+        mp.max_len = max_len; mp.max_in = S; mp.tp = e->t; mp.vocab = c.vocab_size;
+        mp.eps = c.layernorm_eps; mp.inv_sqrt_dh = 1.f / std::sqrt((float)dh);
+        if (mega_plan(mp, c.int8_mode == 1) != FTCF_OK) e->mega_on = false;
+    }
+    if (e->mega_on) {
+        mg::Params& mp = e->mega;
+        FTCF_TRY(e->ffn_part.ensure((size_t)mp.ks * B * e->h * 4));
+        FTCF_TRY(e->att_part.ensure((size_t)B * e->Hl * mp.att_max_units * (dh + 2) * 4 + 256));
+        mp.wte = e->wte; mp.lnf_g = e->lnf_g; mp.lnf_b = e->lnf_b; mp.lm_head = e->lm_head;
+        mp.logits = e->logits.as<float>(); mp.ld_logits = e->Vp;
+        mp.x = e->x.as<__half>(); mp.qkv = e->qkv.as<__half>(); mp.inter_buf = e->inter.as<__half>(); mp.ctx = e->ctx.as<__half>();
+        mp.ffn_part = e->ffn_part.as<float>(); mp.att_part = e->att_part.as<float>();
+        mp.kv = e->kv.as<__half>(); mp.kv_layer_elems = per_layer;
+        mp.gbar = e->gbar.as<unsigned>();
+    }
 
     // small slab layout
     Small s{};

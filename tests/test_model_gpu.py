@@ -17,12 +17,16 @@ pytestmark = pytest.mark.gpu
 LOGIT_RTOL, LOGIT_ATOL = 2e-2, 3e-2
 
 
-def _build(cfg, int8_mode, cuda, seed=0):
+def _build(cfg, int8_mode, cuda, seed=0, mega=1, tweak=None):
+    """mega = 1: the persistent decode-step kernel (decode_mega.cu) where it applies; 0: one kernel per operator."""
     rw = W.make_synthetic(cfg, 1, 0, int8_mode, "cpu", seed=seed, keep_plain=True)
+    if tweak is not None:
+        tweak(rw)
     ref = oracle_from_rank_weights(cfg, [rw], int8_mode)
     w, q, s = to_cuda_lists(rw, cuda)
     op = GptNeoXOp(None, 0, cfg.head_num, cfg.size_per_head, cfg.inter_size, cfg.layer_num, cfg.vocab_size,
                    cfg.rotary_embedding_dim, cfg.start_id, cfg.end_id, 1, 1, int8_mode, 1024, cfg.use_gptj_residual, w, q, s)
+    op.set_option("mega", mega)
     return op, ref
 
 
@@ -48,8 +52,10 @@ def _compare(op, ref, cuda, ids, lens, out_len, graph, **kw):
                       repetition_penalty=kw.get("repetition_penalty"), random_seed=kw.get("random_seed"),
                       return_cum_log_probs=kw.get("return_cum_log_probs", 0), keep_logits=True)
     if trace is not None:
+        n_gen = exp["sequence_lengths"].reshape(-1) - S
         for i, lg in enumerate(exp["logits"]):
-            assert_close(f"logits step {i}", trace[i].cpu().numpy(), lg, LOGIT_RTOL, LOGIT_ATOL)
+            live = n_gen > i          # a finished row skips attention (template.hpp:1176-1178): its logits are don't-care
+            assert_close(f"logits step {i}", trace[i].cpu().numpy()[live], lg[live], LOGIT_RTOL, LOGIT_ATOL)
     assert np.array_equal(res[0].cpu().numpy(), exp["output_ids"]), (res[0].cpu().numpy(), exp["output_ids"])
     assert np.array_equal(res[1].cpu().numpy(), exp["sequence_lengths"])
     if kw.get("return_cum_log_probs", 0):
@@ -57,19 +63,21 @@ def _compare(op, ref, cuda, ids, lens, out_len, graph, **kw):
     return res, exp
 
 
+@pytest.mark.parametrize("mega", [0, 1])
 @pytest.mark.parametrize("int8_mode", [0, 1])
 @pytest.mark.parametrize("graph", [False, True])
-def test_greedy_full_batch(cuda, int8_mode, graph):
+def test_greedy_full_batch(cuda, int8_mode, graph, mega):
     cfg = tiny_cfg()
-    op, ref = _build(cfg, int8_mode, cuda)
+    op, ref = _build(cfg, int8_mode, cuda, mega=mega)
     ids = _prompts(2, 12, cfg.vocab_size, [12, 12])
     _compare(op, ref, cuda, ids, [12, 12], 10, graph)
 
 
+@pytest.mark.parametrize("mega", [0, 1])
 @pytest.mark.parametrize("int8_mode", [0, 1])
-def test_greedy_ragged_batch(cuda, int8_mode):
+def test_greedy_ragged_batch(cuda, int8_mode, mega):
     cfg = tiny_cfg()
-    op, ref = _build(cfg, int8_mode, cuda, seed=3)
+    op, ref = _build(cfg, int8_mode, cuda, seed=3, mega=mega)
     lens = [16, 5, 11, 1]
     ids = _prompts(4, 16, cfg.vocab_size, lens, seed=7)
     _compare(op, ref, cuda, ids, lens, 8, False)
@@ -84,29 +92,68 @@ def test_sequential_residual(cuda):
     _compare(op, ref, cuda, ids, lens, 6, False)
 
 
-def test_dh128_full_rotary(cuda):
+@pytest.mark.parametrize("mega", [0, 1])
+def test_dh128_full_rotary(cuda, mega):
     cfg = tiny_cfg(head_num=2, size_per_head=128, rotary_embedding_dim=128, inter_size=1024, layer_num=3)
-    op, ref = _build(cfg, 1, cuda, seed=11)
+    op, ref = _build(cfg, 1, cuda, seed=11, mega=mega)
     lens = [20, 13]
     ids = _prompts(2, 20, cfg.vocab_size, lens, seed=2)
     _compare(op, ref, cuda, ids, lens, 12, False)
     _compare(op, ref, cuda, ids, lens, 12, True)
 
 
-def test_seeded_topk_sampling_and_cum_log_probs(cuda):
+@pytest.mark.parametrize("mega", [0, 1])
+def test_seeded_topk_sampling_and_cum_log_probs(cuda, mega):
     cfg = tiny_cfg()
-    op, ref = _build(cfg, 1, cuda, seed=1)
+    op, ref = _build(cfg, 1, cuda, seed=1, mega=mega)
     lens = [10, 7, 10]
     ids = _prompts(3, 10, cfg.vocab_size, lens, seed=4)
     _compare(op, ref, cuda, ids, lens, 8, False, top_k=[8, 8, 8], top_p=[0.9, 0.9, 0.9], temperature=[0.7, 0.7, 0.7],
              repetition_penalty=[1.1, 1.1, 1.1], random_seed=[42, 42, 43], return_cum_log_probs=1)
 
 
-def test_single_token_prompt_runs_decoder_only(cuda):
+@pytest.mark.parametrize("mega", [0, 1])
+def test_single_token_prompt_runs_decoder_only(cuda, mega):
     cfg = tiny_cfg()
-    op, ref = _build(cfg, 1, cuda, seed=2)
+    op, ref = _build(cfg, 1, cuda, seed=2, mega=mega)
     ids = _prompts(2, 1, cfg.vocab_size, [1, 1], seed=3)
     _compare(op, ref, cuda, ids, [1, 1], 6, False)
+
+
+@pytest.mark.parametrize("int8_mode", [0, 1])
+def test_mega_long_context_batch8(cuda, int8_mode):
+    """The persistent decode kernel with several attention work units per head (context > 160 keys), KV tiles that straddle
+    the pad gap of ragged prompts, 8 sequences (all 8 MMA columns live), k extents of 3 and 12 k-steps and a head count that
+    does not divide the CTA count."""
+    cfg = tiny_cfg(head_num=6, size_per_head=64, inter_size=1536, layer_num=2, vocab_size=640, rotary_embedding_dim=16, end_id=639)
+    op, ref = _build(cfg, int8_mode, cuda, seed=21, mega=1)
+    lens = [230, 1, 97, 230, 161, 64, 200, 33]
+    ids = _prompts(8, 230, cfg.vocab_size, lens, seed=5)
+    _compare(op, ref, cuda, ids, lens, 5, False)
+    res_g, _ = _compare(op, ref, cuda, ids, lens, 5, True)
+    # the per-operator path must agree with the persistent kernel on every id
+    op.set_option("mega", 0)
+    res_k = op.forward(torch.from_numpy(ids).to(cuda), torch.tensor(lens, dtype=torch.int32, device=cuda), 5)
+    assert torch.equal(res_g[0], res_k[0])
+
+
+@pytest.mark.parametrize("mega", [0, 1])
+def test_finished_rows_stop_advancing(cuda, mega):
+    """Rows that sample end_id stop (their attention work disappears from the schedule, the sampler pins them to end_id)
+    while the others go on; the request ends early once every row is finished.  The end_id row of the LM head is scaled up
+    so that end_id wins within a few steps for some rows."""
+    cfg = tiny_cfg()
+
+    def tweak(rw):
+        rw.w[12 * cfg.layer_num + 3][cfg.end_id] *= 6.0
+
+    op, ref = _build(cfg, 1, cuda, seed=6, mega=mega, tweak=tweak)
+    lens = [6, 6, 3, 5]
+    ids = _prompts(4, 6, cfg.vocab_size, lens, seed=8)
+    res, exp = _compare(op, ref, cuda, ids, lens, 16, False, top_k=[6, 6, 6, 6], top_p=[1.0] * 4, random_seed=[1, 2, 3, 4])
+    n_gen = exp["sequence_lengths"].reshape(-1) - 6
+    assert n_gen.min() < 16, "the tweak did not make any row finish early: the test would not cover finished rows"
+    _compare(op, ref, cuda, ids, lens, 16, True, top_k=[6, 6, 6, 6], top_p=[1.0] * 4, random_seed=[1, 2, 3, 4])
 
 
 def test_streaming_callback_and_early_stop(cuda):
