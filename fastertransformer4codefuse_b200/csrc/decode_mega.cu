@@ -40,10 +40,24 @@ namespace mg {
 using namespace tma;
 
 // ------------------------------------------------------------------------------------------------ small device helpers
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+// streamed-once data (weights, KV): L2 evict_first, so that the activations / barrier words the consumers re-read stay resident
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol)
+{
+    if (pol == 0) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                     "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                     : "memory");
+        return;
+    }
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                  : "memory");
 }
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // consumer warps only
@@ -57,6 +71,20 @@ __device__ __forceinline__ float ld_cg_f32(const float* p)
 {
     float r;
     asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+// raw 16-bit loads whose ISSUE point is pinned (asm volatile) and whose VALUE is not touched until the caller converts it:
+// used to request epilogue operands a whole unit ahead of their use
+__device__ __forceinline__ unsigned short ld_nc_u16_raw(const void* p)
+{
+    unsigned short r;
+    asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned short ld_cg_u16_raw(const void* p)
+{
+    unsigned short r;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p));
     return r;
 }
 __device__ __forceinline__ __half ld_cg_h(const __half* p)
@@ -117,6 +145,17 @@ struct RingPos {
         }
     }
 };
+// producer only: before issuing stage i, stage i - inflight must have LANDED.  The ring still buffers `ns` stages of skew, but
+// no more than `inflight` copies per SM queue up in the memory system -- with 148 SMs x 12 x 16 KB outstanding every dependent
+// L2 access of the consumers (grid barrier, operand staging) waited microseconds behind the prefetch stream.
+struct Smem;
+struct Throttle {
+    RingPos tail;      // oldest stage that may still be in flight
+    int ahead;         // stages issued and not yet known to have landed
+    uint64_t pol;
+    long long c_empty, c_thr;   // dbg & 64 accounting
+};
+__device__ __forceinline__ void throttle_before_issue(Throttle& th, Smem& sm, const Params& p);
 
 // per-sequence attention bookkeeping, identical in every CTA (derived from device-resident request state)
 struct AttInfo {
@@ -140,46 +179,62 @@ struct Smem {
     __align__(16) __half knew[128];
     __align__(16) __half vnew[128];
     const __half* src[MAX_B];
+    long long c_full[CW];
     float s_new;
     int flag;
 };
 
 // ------------------------------------------------------------------------------------------------ producer
-__device__ __forceinline__ void produce_weight_unit(const Params& p, uint8_t* ring, Smem& sm, RingPos& rp, const uint8_t* src,
-                                                    size_t row_stride, int nrows, int kbytes, int lane)
+// one weight unit = consecutive 16-row blocks of the tiled layout: one contiguous bulk copy per stage
+__device__ __forceinline__ void throttle_before_issue(Throttle& th, Smem& sm, const Params& p)
+{
+    if (th.ahead >= p.inflight) {
+        const long long t0 = clock64();
+        mbar_wait(&sm.full[th.tail.slot], th.tail.par);   // completes when that stage's bytes have arrived
+        th.c_thr += clock64() - t0;
+        th.tail.next(p.ns);
+        --th.ahead;
+    }
+    ++th.ahead;
+}
+
+__device__ __forceinline__ void produce_weight_unit(const Params& p, uint8_t* ring, Smem& sm, RingPos& rp, Throttle& th, const uint8_t* src,
+                                                    int kbytes, int lane)
 {
     for (int k0 = 0; k0 < kbytes; k0 += STAGE_K) {
-        const int bytes = min(STAGE_K, kbytes - k0);
+        const uint32_t bytes = (uint32_t)(ROWS * min(STAGE_K, kbytes - k0));
         if (lane == 0) {
+            throttle_before_issue(th, sm, p);
+            const long long t0 = clock64();
             mbar_wait(&sm.empty[rp.slot], rp.par ^ 1);
-            mbar_arrive_expect_tx(&sm.full[rp.slot], (uint32_t)(nrows * bytes));
+            th.c_empty += clock64() - t0;
+            mbar_arrive_expect_tx(&sm.full[rp.slot], bytes);
+            bulk_g2s(ring + (size_t)rp.slot * STAGE_BYTES, src + (size_t)k0 * ROWS, bytes, &sm.full[rp.slot], th.pol);
         }
-        __syncwarp();
-        if (lane < nrows)
-            bulk_g2s(ring + (size_t)rp.slot * STAGE_BYTES + lane * ROW_PITCH, src + (size_t)lane * row_stride + k0, (uint32_t)bytes,
-                     &sm.full[rp.slot]);
         rp.next(p.ns);
     }
+    __syncwarp();
 }
 
 // rows [tv, tv + nk) of the virtual (gap-free) key index space of (b, head) -> one stage
-__device__ __forceinline__ void produce_kv_tile(const Params& p, uint8_t* ring, Smem& sm, RingPos& rp, const __half* cache_bh, int b,
-                                                int tv, int nk, int lane)
+__device__ __forceinline__ void produce_kv_tile(const Params& p, uint8_t* ring, Smem& sm, RingPos& rp, Throttle& th, const __half* cache_bh,
+                                                int b, int tv, int nk, int lane)
 {
     const int rowb = p.dh * 2;
     const int inl = sm.att.inl[b];
     if (lane == 0) {
+        throttle_before_issue(th, sm, p);
         mbar_wait(&sm.empty[rp.slot], rp.par ^ 1);
         mbar_arrive_expect_tx(&sm.full[rp.slot], (uint32_t)(nk * rowb));
         uint8_t* dst = ring + (size_t)rp.slot * STAGE_BYTES;
         int n1 = 0;
         if (tv < inl) {
             n1 = min(nk, inl - tv);
-            bulk_g2s(dst, cache_bh + (size_t)tv * p.dh, (uint32_t)(n1 * rowb), &sm.full[rp.slot]);
+            bulk_g2s(dst, cache_bh + (size_t)tv * p.dh, (uint32_t)(n1 * rowb), &sm.full[rp.slot], th.pol);
         }
         if (n1 < nk) {
             const int pos = (tv + n1) - inl + p.max_in;   // past the pad gap [input_len, max_in)
-            bulk_g2s(dst + (size_t)n1 * rowb, cache_bh + (size_t)pos * p.dh, (uint32_t)((nk - n1) * rowb), &sm.full[rp.slot]);
+            bulk_g2s(dst + (size_t)n1 * rowb, cache_bh + (size_t)pos * p.dh, (uint32_t)((nk - n1) * rowb), &sm.full[rp.slot], th.pol);
         }
     }
     __syncwarp();
@@ -187,59 +242,64 @@ __device__ __forceinline__ void produce_kv_tile(const Params& p, uint8_t* ring, 
 }
 
 // ------------------------------------------------------------------------------------------------ consumer: GEMM units
+// register image of one ring stage for one warp: its 128-byte k-step of the 16 weight rows and the matching activations
 template <typename WT>
-__device__ __forceinline__ void gemm_stage(const uint8_t* slot, uint64_t* full, uint64_t* empty, uint32_t par, int bytes,
-                                           const uint8_t* opnd_row, int kelem0, int warp, int lane, float (&acc)[4])
+struct Frag {
+    uint4 x[16 / (int)sizeof(WT) / 4];
+    uint4 w[2][2];
+};
+
+template <typename WT>
+__device__ __forceinline__ void frag_load_x(Frag<WT>& f, const uint8_t* opnd_row, int kelem0, int warp, int t)
 {
     constexpr int EPC = 16 / (int)sizeof(WT);   // k elements per 16-byte weight chunk
     constexpr int KSTEP = 8 * EPC;              // k elements per 128-byte k-step
+    const int j0 = (kelem0 + warp * KSTEP + t * 2 * EPC) >> 3;
+#pragma unroll
+    for (int q = 0; q < EPC / 4; ++q) f.x[q] = *reinterpret_cast<const uint4*>(opnd_row + (swz(j0 + q) << 4));
+}
+template <typename WT>
+__device__ __forceinline__ void frag_load_w(Frag<WT>& f, const uint8_t* slot, int bytes, int warp, int g, int t)
+{
+    // block image: row r at r * bytes, 16-byte chunk c at chunk c ^ (r & 7)   ((g + 8) & 7 == g & 7)
+    const uint8_t* st = slot + g * bytes + warp * 128;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) f.w[hh][c] = *reinterpret_cast<const uint4*>(st + hh * 8 * bytes + (((2 * t + c) ^ (g & 7)) << 4));
+}
+// two independent accumulator chains (one per 16-byte chunk) so that consecutive MMAs do not wait for each other
+template <typename WT>
+__device__ __forceinline__ void frag_mma(const Frag<WT>& f, float (&acc0)[4], float (&acc1)[4])
+{
+    constexpr int EPC = 16 / (int)sizeof(WT);
     constexpr int NMMA = EPC / 4;
-    constexpr int XV = EPC / 4;                 // uint4 of activations per lane per k-step
-    const int g = lane >> 2, t = lane & 3;
-    const bool active = warp * 128 < bytes;
-    uint4 xv[XV];
-    if (active) {
-        const int j0 = (kelem0 + warp * KSTEP + t * 2 * EPC) >> 3;
 #pragma unroll
-        for (int q = 0; q < XV; ++q) xv[q] = *reinterpret_cast<const uint4*>(opnd_row + (swz(j0 + q) << 4));
-    }
-    mbar_wait(full, par);
-    if (active) {
-        const uint8_t* st = slot + g * ROW_PITCH + warp * 128 + t * 32;
-        uint4 wv[2][2];
+    for (int j = 0; j < NMMA; ++j)
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) wv[hh][c] = *reinterpret_cast<const uint4*>(st + hh * 8 * ROW_PITCH + c * 16);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty);
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int j = 0; j < NMMA; ++j) {
-                const int pi = c * (EPC / 2) + 2 * j;
-                uint32_t a0, a1, a2, a3;
-                if constexpr (sizeof(WT) == 1) {
-                    u8x4_to_h2x2(u4_get(wv[0][c], j), a0, a2);
-                    u8x4_to_h2x2(u4_get(wv[1][c], j), a1, a3);
-                } else {
-                    a0 = u4_get(wv[0][c], 2 * j);
-                    a2 = u4_get(wv[0][c], 2 * j + 1);
-                    a1 = u4_get(wv[1][c], 2 * j);
-                    a3 = u4_get(wv[1][c], 2 * j + 1);
-                }
-                mma_16816(acc, a0, a1, a2, a3, u4_get(xv[pi / 4], pi % 4), u4_get(xv[(pi + 1) / 4], (pi + 1) % 4));
+        for (int c = 0; c < 2; ++c) {
+            const int pi = c * (EPC / 2) + 2 * j;
+            uint32_t a0, a1, a2, a3;
+            if constexpr (sizeof(WT) == 1) {
+                u8x4_to_h2x2(u4_get(f.w[0][c], j), a0, a2);
+                u8x4_to_h2x2(u4_get(f.w[1][c], j), a1, a3);
+            } else {
+                a0 = u4_get(f.w[0][c], 2 * j);
+                a2 = u4_get(f.w[0][c], 2 * j + 1);
+                a1 = u4_get(f.w[1][c], 2 * j);
+                a3 = u4_get(f.w[1][c], 2 * j + 1);
             }
-    } else {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty);
-    }
+            if (c == 0) mma_16816(acc0, a0, a1, a2, a3, u4_get(f.x[pi / 4], pi % 4), u4_get(f.x[(pi + 1) / 4], (pi + 1) % 4));
+            else mma_16816(acc1, a0, a1, a2, a3, u4_get(f.x[pi / 4], pi % 4), u4_get(f.x[(pi + 1) / 4], (pi + 1) % 4));
+        }
 }
 
 enum { EP_QKV = 0, EP_FFN1 = 1, EP_FFN2 = 2, EP_O = 3, EP_LM = 4 };
 
-// One weight unit: 16 rows [row0, row0 + 16) x kbytes of k starting at operand element kelem_base; leaves the 16 x B results
-// (summed over the 8 k-splitting warps, fixed order) with threads 0..127 and runs the epilogue `ep` there.
+// One weight unit: 16 rows [row0, row0 + 16) x kbytes of k (operand elements from 0); leaves the 16 x B results (summed over
+// the 8 k-splitting warps, fixed order) with threads 0..127 and runs the epilogue `ep` there.  The stage loop is software
+// pipelined (the next stage's barrier wait and shared-memory loads are issued before the current stage's MMAs) and the
+// epilogue's global operands are requested before the loop, so neither latency sits on the unit's critical path.
 template <typename WT, bool W8>
 __device__ __forceinline__ void gemm_unit(const Params& p, const LayerDev* Ld, uint8_t* ring, Smem& sm, RingPos& rp, int& redbuf,
                                           const uint8_t* opnd, int kbytes, int row0, int nrows_total, int ep, int kc, int warp,
@@ -247,13 +307,74 @@ __device__ __forceinline__ void gemm_unit(const Params& p, const LayerDev* Ld, u
 {
     const int tid = warp * 32 + lane;
     const int g = lane >> 2, t = lane & 3;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const uint8_t* opnd_row = opnd + (size_t)min(g, p.B - 1) * p.opnd_pitch;
-    for (int k0 = 0; k0 < kbytes; k0 += STAGE_K) {
-        gemm_stage<WT>(ring + (size_t)rp.slot * STAGE_BYTES, &sm.full[rp.slot], &sm.empty[rp.slot], rp.par, min(STAGE_K, kbytes - k0),
-                       opnd_row, k0 / (int)sizeof(WT), warp, lane, acc);
-        rp.next(p.ns);
+
+    // ---- epilogue operands, requested early
+    const int f = tid & 15, tok = tid >> 4;
+    const int col = row0 + f;
+    const bool ep_thread = tid < 128 && tok < p.B && col < nrows_total;
+    // (raw bits only here: touching a value would stall this warp for a DRAM latency at the START of every unit and, through
+    // the unit-end barrier, all the others with it)
+    constexpr int MAX_KS_PF = 4;
+    unsigned short raw_scale = 0x3c00 /* 1.0 */, raw_b = 0, raw_xs = 0;
+    float raw_ffn[MAX_KS_PF] = {0.f, 0.f, 0.f, 0.f};
+    if (ep_thread && ep != EP_LM) {
+        const int kind = ep == EP_QKV ? 0 : (ep == EP_O ? 1 : (ep == EP_FFN1 ? 2 : 3));
+        if constexpr (W8) raw_scale = ld_nc_u16_raw(Ld->scale[kind] + col);
+        if (ep == EP_FFN1) raw_b = ld_nc_u16_raw(Ld->ffn1_b + col);
+        if (ep == EP_O) {
+            raw_b = ld_nc_u16_raw(Ld->res_b + col);
+            raw_xs = ld_cg_u16_raw(sm.xrow[tok] + col);
+            if (p.ks <= MAX_KS_PF) {
+#pragma unroll
+                for (int c2 = 0; c2 < MAX_KS_PF; ++c2)
+                    if (c2 < p.ks) raw_ffn[c2] = ld_cg_f32(p.ffn_part + ((size_t)c2 * p.B + tok) * p.h + col);
+            }
+        }
     }
+
+    // ---- pipelined stage loop
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+    const int nst = (kbytes + STAGE_K - 1) / STAGE_K;
+    auto load_stage = [&](Frag<WT>& fr, int s) -> bool {
+        const int bytes = min(STAGE_K, kbytes - s * STAGE_K);
+        const bool active = warp * 128 < bytes;
+        if (active && !(p.dbg & 16)) frag_load_x<WT>(fr, opnd_row, s * (STAGE_K / (int)sizeof(WT)), warp, t);
+        if (p.dbg & 64) {
+            const long long t0 = clock64();
+            mbar_wait(&sm.full[rp.slot], rp.par);
+            sm.c_full[warp] += clock64() - t0;
+        } else {
+            mbar_wait(&sm.full[rp.slot], rp.par);
+        }
+        if (active && !(p.dbg & 16)) frag_load_w<WT>(fr, ring + (size_t)rp.slot * STAGE_BYTES, bytes, warp, g, t);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[rp.slot]);
+        rp.next(p.ns);
+        return active;
+    };
+    Frag<WT> f0, f1;
+    if (p.dbg & 17) {
+#pragma unroll
+        for (int q = 0; q < 16 / (int)sizeof(WT) / 4; ++q) f0.x[q] = f1.x[q] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) f0.w[q >> 1][q & 1] = f1.w[q >> 1][q & 1] = make_uint4(0, 0, 0, 0);
+    }
+    const bool do_mma = !(p.dbg & 1);
+    bool a0 = load_stage(f0, 0), a1 = false;
+    for (int s = 0; s < nst; s += 2) {
+        a1 = (s + 1 < nst) ? load_stage(f1, s + 1) : false;
+        if (a0 && do_mma) frag_mma<WT>(f0, acc, acc1);
+        a0 = (s + 2 < nst) ? load_stage(f0, s + 2) : false;
+        if (a1 && do_mma) frag_mma<WT>(f1, acc, acc1);
+    }
+    if (p.dbg & 8) {
+        if (acc[0] + acc1[0] + __uint_as_float(f0.w[0][0].x ^ f1.w[0][0].x) == 123.456f) p.logits[0] = 1.f;   // keep the loads alive
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] += acc1[i];
+
     float(*red)[8][RED_PITCH] = sm.red[redbuf];
     red[warp][2 * t][g] = acc[0];
     red[warp][2 * t + 1][g] = acc[1];
@@ -261,10 +382,7 @@ __device__ __forceinline__ void gemm_unit(const Params& p, const LayerDev* Ld, u
     red[warp][2 * t + 1][g + 8] = acc[3];
     cbar();
     redbuf ^= 1;
-    if (tid >= 128) return;
-    const int f = tid & 15, tok = tid >> 4;
-    const int col = row0 + f;
-    if (tok >= p.B || col >= nrows_total) return;
+    if (!ep_thread) return;
     float v = red[0][tok][f];
 #pragma unroll
     for (int w = 1; w < CW; ++w) v += red[w][tok][f];
@@ -272,28 +390,34 @@ __device__ __forceinline__ void gemm_unit(const Params& p, const LayerDev* Ld, u
         p.logits[(size_t)tok * p.ld_logits + col] = v;
         return;
     }
-    const int kind = ep == EP_QKV ? 0 : (ep == EP_O ? 1 : (ep == EP_FFN1 ? 2 : 3));
-    if constexpr (W8) v *= __half2float(Ld->scale[kind][col]);
+    const float pf_scale = __half2float(__ushort_as_half(raw_scale));
+    const __half pf_b = __ushort_as_half(raw_b), pf_xs = __ushort_as_half(raw_xs);
+    v *= pf_scale;
     if (ep == EP_QKV) {
         p.qkv[(size_t)tok * 3 * p.hl + col] = __float2half_rn(v);
     } else if (ep == EP_FFN1) {
         __half o;
         if constexpr (W8) {
-            v += __half2float(Ld->ffn1_b[col]);
+            v += __half2float(pf_b);
             o = __float2half_rn(gelu_tanh_f32(v));
         } else {
-            o = gelu_tanh_half_ref(__hadd(__float2half_rn(v), Ld->ffn1_b[col]));
+            o = gelu_tanh_half_ref(__hadd(__float2half_rn(v), pf_b));
         }
         p.inter_buf[(size_t)tok * p.inter + col] = o;
     } else if (ep == EP_FFN2) {
         p.ffn_part[((size_t)kc * p.B + tok) * p.h + col] = v;
     } else {   // EP_O: x <- ((ffn + attn) + bias) + x / tp      (add_residual_kernels.cu:116-152, fp16 adds)
         const __half attn = __float2half_rn(v);
-        float fs = 0.f;
-        for (int c2 = 0; c2 < p.ks; ++c2) fs += ld_cg_f32(p.ffn_part + ((size_t)c2 * p.B + tok) * p.h + col);
-        __half r = __hadd(__float2half_rn(fs), attn);
-        r = __hadd(r, Ld->res_b[col]);
-        __half xs = ld_cg_h(sm.xrow[tok] + col);
+        float pf_ffn = 0.f;
+        if (p.ks <= MAX_KS_PF) {
+#pragma unroll
+            for (int c2 = 0; c2 < MAX_KS_PF; ++c2) pf_ffn += raw_ffn[c2];   // unused slots are 0; fixed order
+        } else {
+            for (int c2 = 0; c2 < p.ks; ++c2) pf_ffn += ld_cg_f32(p.ffn_part + ((size_t)c2 * p.B + tok) * p.h + col);
+        }
+        __half r = __hadd(__float2half_rn(pf_ffn), attn);
+        r = __hadd(r, pf_b);
+        __half xs = pf_xs;
         if (p.tp > 1) xs = __float2half_rn(__half2float(xs) * (1.f / (float)p.tp));
         p.x[(size_t)tok * p.h + col] = __hadd(r, xs);
     }
@@ -342,6 +466,7 @@ __device__ __forceinline__ void stage_layernorm(const Params& p, uint8_t* opnd, 
                                                 bool have_stats, int warp, int lane)
 {
     const int tid = warp * 32 + lane;
+    if (p.dbg & 32) return;
     stage_rows(p, opnd, sm.xrow, 0, p.h, tid);
     cbar();
     if (!have_stats) {
@@ -367,10 +492,28 @@ __device__ __forceinline__ void stage_layernorm(const Params& p, uint8_t* opnd, 
 }
 
 // ------------------------------------------------------------------------------------------------ grid barrier
-__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target, int tid)
+constexpr int TS_BARS = 130, TS_CTAS = 160;
+__device__ unsigned long long g_mega_ts[3][TS_BARS][TS_CTAS];
+__device__ long long g_mega_cyc[8][TS_CTAS];   // dbg & 64: per CTA cycles [0] producer empty-wait [1] producer throttle-wait [2] producer total
+                                               // [3] consumer warp 0 full-wait [4] consumer total [5] consumer cbar-wait [6] stages   // dbg & 64: globaltimer at [enter, arrive, release] of each barrier
+__device__ __forceinline__ unsigned long long gtime()
 {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target, int tid, int dbg)
+{
+    if (dbg & 2) {
+        cbar();
+        return;
+    }
+    const bool ts = (dbg & 64) && tid == 0 && target / gridDim.x <= TS_BARS && blockIdx.x < TS_CTAS;
+    const unsigned bi = target / gridDim.x - 1;
+    if (ts) g_mega_ts[0][bi][blockIdx.x] = gtime();
     __threadfence();
     cbar();
+    if (ts) g_mega_ts[1][bi][blockIdx.x] = gtime();
     if (tid == 0) {
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         unsigned v = 0;
@@ -383,6 +526,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target, int
         } while (true);
         __threadfence();
     }
+    if (ts) g_mega_ts[2][bi][blockIdx.x] = gtime();
     cbar();
 }
 
@@ -637,8 +781,9 @@ template <bool W8, int DH>
 __global__ void __launch_bounds__(THREADS, 1) decode_mega_kernel(const __grid_constant__ Params p)
 {
     using WT = typename std::conditional<W8, uint8_t, __half>::type;
+    // NOTE: no integer round trip on this pointer -- the compiler must keep seeing shared memory (LDS/STS, not generic LD/ST)
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* ring = smem_raw;
     uint8_t* opnd = ring + (size_t)p.ns * STAGE_BYTES;
     Smem& sm = *reinterpret_cast<Smem*>(opnd + (size_t)p.B * p.opnd_pitch);
 
@@ -673,15 +818,21 @@ __global__ void __launch_bounds__(THREADS, 1) decode_mega_kernel(const __grid_co
     }
     __syncthreads();
 
-    const int NA = sm.att.pre[p.B];
+    const int NA = (p.dbg & 4) ? 0 : sm.att.pre[p.B];
     const int Tq = (3 * p.hl + ROWS - 1) / ROWS, Tf1 = (p.inter + ROWS - 1) / ROWS, Th = (p.h + ROWS - 1) / ROWS;
     const int hB = p.h * wsz, hlB = p.hl * wsz, interB = p.inter * wsz;
     const int KU = p.ks > 1 ? hB : interB;      // FFN2 k bytes per unit
     RingPos rp{0, 0};
     int phase = 0;
 
-    if (warp == CW) {
+    if (warp >= CW) {
         // ======================================= producer =======================================
+        // register budget: the CTA owns 384 x 168; the producer warpgroup keeps 40 per thread and the 256 consumer threads may
+        // then grow to 168 + 128 x (168 - 40) / 256 = 232 (asking for more would block forever)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp != CW) return;
+        Throttle th{RingPos{0, 0}, 0, (p.dbg & 128) ? 0ull : l2_evict_first_policy(), 0, 0};
+        const long long t_start = clock64();
         for (int l = p.l0; l < p.l1; ++l) {
             const LayerDev* Ld = p.layers + l;
             int u0, u1;
@@ -690,9 +841,8 @@ __global__ void __launch_bounds__(THREADS, 1) decode_mega_kernel(const __grid_co
             for (int u = u0; u < u1; ++u) {
                 const bool is_q = u < Tq;
                 const int row0 = (is_q ? u : u - Tq) * ROWS;
-                const int nrows = min(ROWS, (is_q ? 3 * p.hl : p.inter) - row0);
                 const uint8_t* W = static_cast<const uint8_t*>(Ld->w[is_q ? 0 : 2]);
-                produce_weight_unit(p, ring, sm, rp, W + (size_t)row0 * hB, hB, nrows, hB, lane);
+                produce_weight_unit(p, ring, sm, rp, th, W + (size_t)row0 * hB, hB, lane);
             }
             // phase B: attention units, then FFN2 split-k tiles
             my_range(NA + p.ks * Th, phase++ * 53, u0, u1);
@@ -705,15 +855,13 @@ __global__ void __launch_bounds__(THREADS, 1) decode_mega_kernel(const __grid_co
                     const int v0 = j * ATT_UNIT, v1 = min(sm.att.nvalid[b], v0 + ATT_UNIT);
                     for (int tv = v0; tv < v1; tv += ATT_TILE) {
                         const int nk = min(ATT_TILE, v1 - tv);
-                        produce_kv_tile(p, ring, sm, rp, kc, b, tv, nk, lane);
-                        produce_kv_tile(p, ring, sm, rp, vc, b, tv, nk, lane);
+                        produce_kv_tile(p, ring, sm, rp, th, kc, b, tv, nk, lane);
+                        produce_kv_tile(p, ring, sm, rp, th, vc, b, tv, nk, lane);
                     }
                 } else {
                     const int kc = (u - NA) / Th, row0 = ((u - NA) % Th) * ROWS;
-                    const int nrows = min(ROWS, p.h - row0);
                     const uint8_t* W = static_cast<const uint8_t*>(Ld->w[3]);
-                    produce_weight_unit(p, ring, sm, rp, W + (size_t)row0 * interB + (size_t)kc * KU, interB, nrows,
-                                        min(KU, interB - kc * KU), lane);
+                    produce_weight_unit(p, ring, sm, rp, th, W + (size_t)row0 * interB + (size_t)kc * KU * ROWS, min(KU, interB - kc * KU), lane);
                 }
             }
             // phase C: O-projection tiles (k = hl)
@@ -721,7 +869,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_mega_kernel(const __grid_co
             for (int u = u0; u < u1; ++u) {
                 const int row0 = u * ROWS;
                 const uint8_t* W = static_cast<const uint8_t*>(Ld->w[1]);
-                produce_weight_unit(p, ring, sm, rp, W + (size_t)row0 * hlB, hlB, min(ROWS, p.h - row0), hlB, lane);
+                produce_weight_unit(p, ring, sm, rp, th, W + (size_t)row0 * hlB, hlB, lane);
             }
         }
         if (p.lm_rows > 0) {
@@ -729,16 +877,23 @@ __global__ void __launch_bounds__(THREADS, 1) decode_mega_kernel(const __grid_co
             my_range((p.lm_rows + ROWS - 1) / ROWS, phase++ * 53, u0, u1);
             for (int u = u0; u < u1; ++u) {
                 const int row0 = u * ROWS;
-                produce_weight_unit(p, ring, sm, rp, reinterpret_cast<const uint8_t*>(p.lm_head) + (size_t)row0 * p.h * 2, (size_t)p.h * 2,
-                                    min(ROWS, p.lm_rows - row0), p.h * 2, lane);
+                produce_weight_unit(p, ring, sm, rp, th, static_cast<const uint8_t*>(p.lm_head) + (size_t)row0 * p.h * 2, p.h * 2, lane);
             }
+        }
+        if ((p.dbg & 64) && lane == 0 && blockIdx.x < TS_CTAS) {
+            g_mega_cyc[0][blockIdx.x] = th.c_empty;
+            g_mega_cyc[1][blockIdx.x] = th.c_thr;
+            g_mega_cyc[2][blockIdx.x] = clock64() - t_start;
         }
         return;
     }
 
     // ======================================= consumers =======================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     int redbuf = 0;
     unsigned nbar = 0;
+    const long long t_start_c = clock64();
+    if (lane == 0) sm.c_full[warp] = 0;
     for (int l = p.l0; l < p.l1; ++l) {
         const LayerDev* Ld = p.layers + l;
         int u0, u1;
@@ -760,7 +915,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_mega_kernel(const __grid_co
                 gemm_unit<WT, W8>(p, Ld, ring, sm, rp, redbuf, opnd, hB, row0, is_q ? 3 * p.hl : p.inter, is_q ? EP_QKV : EP_FFN1, 0, warp, lane);
             }
         }
-        grid_barrier(p.gbar, ++nbar * gridDim.x, tid);
+        grid_barrier(p.gbar, ++nbar * gridDim.x, tid, p.dbg);
         // ---------------- phase B
         my_range(NA + p.ks * Th, phase++ * 53, u0, u1);
         {
@@ -785,7 +940,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_mega_kernel(const __grid_co
                 }
             }
         }
-        grid_barrier(p.gbar, ++nbar * gridDim.x, tid);
+        grid_barrier(p.gbar, ++nbar * gridDim.x, tid, p.dbg);
         // ---------------- phase C
         my_range(Th, phase++ * 53, u0, u1);
         if (u1 > u0) {
@@ -795,7 +950,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_mega_kernel(const __grid_co
             cbar();
             for (int u = u0; u < u1; ++u) gemm_unit<WT, W8>(p, Ld, ring, sm, rp, redbuf, opnd, hlB, u * ROWS, p.h, EP_O, 0, warp, lane);
         }
-        grid_barrier(p.gbar, ++nbar * gridDim.x, tid);
+        grid_barrier(p.gbar, ++nbar * gridDim.x, tid, p.dbg);
     }
     if (p.lm_rows > 0) {
         int u0, u1;
@@ -805,11 +960,42 @@ __global__ void __launch_bounds__(THREADS, 1) decode_mega_kernel(const __grid_co
         if (u1 > u0) stage_layernorm(p, opnd, sm, p.lnf_g, p.lnf_b, false, warp, lane);
         for (int u = u0; u < u1; ++u) gemm_unit<__half, false>(p, nullptr, ring, sm, rp, redbuf, opnd, p.h * 2, u * ROWS, p.lm_rows, EP_LM, 0, warp, lane);
     }
+    if ((p.dbg & 64) && lane == 0 && blockIdx.x < TS_CTAS && (warp == 0 || warp == 7)) {
+        g_mega_cyc[warp == 0 ? 3 : 5][blockIdx.x] = sm.c_full[warp];
+        g_mega_cyc[4][blockIdx.x] = clock64() - t_start_c;
+    }
 }
 
 }  // namespace mg
 
 // ------------------------------------------------------------------------------------------------ host side
+__global__ void __launch_bounds__(256) retile_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int n, int kbytes)
+{
+    const int cpr = kbytes >> 4;   // 16-byte chunks per row
+    const size_t total = (size_t)n * cpr;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i / cpr), c_abs = (int)(i % cpr);
+        const int rt = row / mg::ROWS, r = row % mg::ROWS;
+        const int kc = c_abs / (mg::STAGE_K / 16), cw = c_abs % (mg::STAGE_K / 16);
+        const int kw = min(mg::STAGE_K, kbytes - kc * mg::STAGE_K);
+        const size_t off = (size_t)rt * mg::ROWS * kbytes + (size_t)kc * mg::STAGE_BYTES + (size_t)r * kw + ((size_t)(cw ^ (r & 7)) << 4);
+        out[off >> 4] = in[i];
+    }
+}
+
+size_t mega_tiled_bytes(int n, int kbytes) { return (size_t)((n + mg::ROWS - 1) / mg::ROWS) * mg::ROWS * kbytes; }
+
+int mega_retile(const void* w_nk, void* out, int n, int kbytes, cudaStream_t st)
+{
+    FTCF_REQUIRE(w_nk && out && n > 0 && kbytes > 0 && kbytes % 128 == 0, FTCF_ERR_INVALID, "retile: n=%d kbytes=%d", n, kbytes);
+    FTCF_CUDA_CHECK(cudaMemsetAsync(out, 0, mega_tiled_bytes(n, kbytes), st));
+    retile_kernel<<<1184, 256, 0, st>>>(static_cast<const uint4*>(w_nk), static_cast<uint4*>(out), n, kbytes);
+    FTCF_LAUNCH_CHECK();
+    return FTCF_OK;
+}
+
+std::atomic<int> g_mega_dbg{0}, g_mega_ns{0}, g_mega_inflight{4};
+
 bool mega_supported(int B, int h, int hl, int inter, int dh, int rot, bool w8, int tp, bool parallel_residual)
 {
     const int wsz = w8 ? 1 : 2;
@@ -825,7 +1011,7 @@ bool mega_supported(int B, int h, int hl, int inter, int dh, int rot, bool w8, i
 int mega_plan(mg::Params& p, bool w8)
 {
     const int wsz = w8 ? 1 : 2;
-    p.ks = (p.inter % p.h == 0 && p.inter > p.h) ? p.inter / p.h : 1;
+    p.ks = (p.inter % p.h == 0 && p.inter > p.h && (p.h * wsz) % mg::STAGE_K == 0) ? p.inter / p.h : 1;   // split k on block boundaries only
     const int kmax_elems = std::max(std::max(p.h, p.hl), p.ks > 1 ? p.h : p.inter);
     p.opnd_pitch = kmax_elems * 2 + 16;
     p.att_max_units = (p.max_len + mg::ATT_UNIT - 1) / mg::ATT_UNIT + 1;
@@ -835,10 +1021,28 @@ int mega_plan(mg::Params& p, bool w8)
     const long long fixed = (long long)p.B * p.opnd_pitch + (long long)sizeof(mg::Smem) + 256 + 1024 /* static */;
     long long ns = (max_smem - fixed) / mg::STAGE_BYTES;
     if (ns > 16) ns = 16;
+    if (g_mega_ns.load() > 0 && ns > g_mega_ns.load()) ns = g_mega_ns.load();
+    p.inflight = g_mega_inflight.load();
+    if (p.inflight < 1 || p.inflight > ns) p.inflight = (int)ns;
     FTCF_REQUIRE(ns >= 4, FTCF_ERR_UNSUPPORTED, "decode megakernel: batch %d x k %d leaves room for only %lld ring stages", p.B, kmax_elems, ns);
     p.ns = (int)ns;
-    (void)wsz;
     return FTCF_OK;
+}
+
+// diagnostics (not part of include/ftcf.h): copies the barrier timestamps of the last dbg & 64 launch to the host
+extern "C" int ftcf_debug_mega_timestamps(unsigned long long* out, size_t bytes)
+{
+    const size_t want = sizeof(unsigned long long) * 3 * mg::TS_BARS * mg::TS_CTAS;
+    if (bytes < want) return (int)want;
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, mg::g_mega_ts, want) == cudaSuccess ? 0 : -1;
+}
+extern "C" int ftcf_debug_mega_cycles(long long* out, size_t bytes)
+{
+    const size_t want = sizeof(long long) * 8 * mg::TS_CTAS;
+    if (bytes < want) return (int)want;
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, mg::g_mega_cyc, want) == cudaSuccess ? 0 : -1;
 }
 
 size_t mega_smem_bytes(const mg::Params& p)
@@ -846,8 +1050,10 @@ size_t mega_smem_bytes(const mg::Params& p)
     return (size_t)p.ns * mg::STAGE_BYTES + (size_t)p.B * p.opnd_pitch + sizeof(mg::Smem) + 256;
 }
 
-int mega_launch(const mg::Params& p, bool w8, cudaStream_t st)
+int mega_launch(const mg::Params& p_in, bool w8, cudaStream_t st)
 {
+    mg::Params p = p_in;
+    p.dbg = g_mega_dbg.load(std::memory_order_relaxed);
     int dev = 0, sms = 0;
     FTCF_CUDA_CHECK(cudaGetDevice(&dev));
     FTCF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

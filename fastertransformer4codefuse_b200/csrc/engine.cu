@@ -172,7 +172,8 @@ struct ftcf_gptneox {
     DevBuf kv, x, x2, n1, n2, qkv, qbuf, ctx, attn, inter, ffn, logits, logits_local, logits_gather, samp_ws, small, mmha_part,
         prompt_meta, lm_pad, layer_dev, ffn_part, att_part, gbar;
     mg::Params mega{};                  // persistent decode-step kernel arguments of the current request
-    bool mega_on = false;
+    bool mega_on = false, mega_weights = false;
+    const void* lm_head_tiled = nullptr;
     int32_t* host_flag = nullptr;       // mapped pinned: [0] finished count, [1] step it belongs to
     int32_t* host_flag_dev = nullptr;
     int32_t* host_stage = nullptr;      // pinned staging for small uploads / callback reads
@@ -379,13 +380,22 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
         }
     }
     if (status == FTCF_OK) {
-        // per-layer pointer table of the persistent decode-step kernel
+        // per-layer pointer table of the persistent decode-step kernel, which streams the weights from a TILED copy
+        // (one contiguous bulk copy per ring stage, decode_mega.cuh)
         std::vector<mg::LayerDev> ld(L);
-        for (int l = 0; l < L; ++l) {
+        const int wsz = c.int8_mode == 1 ? 1 : 2;
+        e->mega_weights = e->opt_mega != 0 && t == 1 && c.use_gptj_residual != 0 &&
+                          mega_supported(1, e->h, e->hl, e->inter_l, c.size_per_head, c.rotary_embedding_dim, c.int8_mode == 1, t, true);
+        for (int l = 0; l < L && status == FTCF_OK; ++l) {
             const LayerW& lw = e->layers[l];
-            for (int kind = 0; kind < 4; ++kind) {
-                ld[l].w[kind] = lw.w[kind];
+            for (int kind = 0; kind < 4 && status == FTCF_OK; ++kind) {
+                ld[l].w[kind] = nullptr;
                 ld[l].scale[kind] = lw.scale[kind];
+                if (!e->mega_weights) continue;
+                e->owned.emplace_back();
+                status = e->owned.back().ensure(mega_tiled_bytes(gn[kind], gk[kind] * wsz));
+                if (status == FTCF_OK) status = mega_retile(lw.w[kind], e->owned.back().p, gn[kind], gk[kind] * wsz, e->stream);
+                ld[l].w[kind] = e->owned.back().p;
             }
             ld[l].ln1_g = lw.ln1_g; ld[l].ln1_b = lw.ln1_b; ld[l].ln2_g = lw.ln2_g; ld[l].ln2_b = lw.ln2_b;
             ld[l].qkv_b = lw.qkv_b; ld[l].ffn1_b = lw.ffn1_b; ld[l].res_b = lw.ffn2_b;
@@ -396,6 +406,12 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
             status = FTCF_ERR_CUDA;
         }
         if (status == FTCF_OK) status = e->gbar.ensure(256);
+        if (status == FTCF_OK && e->mega_weights) {
+            e->owned.emplace_back();
+            status = e->owned.back().ensure(mega_tiled_bytes(e->Vp, e->h * 2));
+            if (status == FTCF_OK) status = mega_retile(e->lm_head, e->owned.back().p, e->Vp, e->h * 2, e->stream);
+            e->lm_head_tiled = e->owned.back().p;
+        }
     }
     if (status == FTCF_OK && t > 1) {
         if (!nccl_unique_id) { set_error("create: tensor_para_size %d needs an NCCL unique id", t); status = FTCF_ERR_INVALID; }
@@ -615,7 +631,7 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     FTCF_TRY(e->samp_ws.ensure(ws_bytes));
     const int splits = ftcf_mmha_choose_splits(B, e->Hl, max_len);
     FTCF_TRY(e->mmha_part.ensure((size_t)B * e->Hl * splits * (dh + 2) * 4 + 256));
-    e->mega_on = e->opt_mega != 0 &&
+    e->mega_on = e->opt_mega != 0 && e->mega_weights &&
                  mega_supported(B, e->h, e->hl, e->inter_l, dh, c.rotary_embedding_dim, c.int8_mode == 1, e->t, c.use_gptj_residual != 0);
     if (e->mega_on) {
         mg::Params& mp = e->mega;
@@ -631,7 +647,7 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
         mg::Params& mp = e->mega;
         FTCF_TRY(e->ffn_part.ensure((size_t)mp.ks * B * e->h * 4));
         FTCF_TRY(e->att_part.ensure((size_t)B * e->Hl * mp.att_max_units * (dh + 2) * 4 + 256));
-        mp.wte = e->wte; mp.lnf_g = e->lnf_g; mp.lnf_b = e->lnf_b; mp.lm_head = e->lm_head;
+        mp.wte = e->wte; mp.lnf_g = e->lnf_g; mp.lnf_b = e->lnf_b; mp.lm_head = e->lm_head_tiled;
         mp.logits = e->logits.as<float>(); mp.ld_logits = e->Vp;
         mp.x = e->x.as<__half>(); mp.qkv = e->qkv.as<__half>(); mp.inter_buf = e->inter.as<__half>(); mp.ctx = e->ctx.as<__half>();
         mp.ffn_part = e->ffn_part.as<float>(); mp.att_part = e->att_part.as<float>();
