@@ -61,7 +61,7 @@ TOKEN_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), 
 class GptNeoXRequest(C.Structure):
     _fields_ = [
         ("input_ids", C.c_void_p), ("input_lengths", C.c_void_p),
-        ("batch", C.c_int32), ("max_input_len", C.c_int32), ("output_len", C.c_int32),
+        ("batch", C.c_int32), ("max_input_len", C.c_int32), ("output_len", C.c_int32), ("beam_width", C.c_int32),
         ("top_k_host", C.c_void_p), ("n_top_k", C.c_int32),
         ("top_p_host", C.c_void_p), ("n_top_p", C.c_int32),
         ("temperature_host", C.c_void_p), ("n_temperature", C.c_int32),

@@ -41,7 +41,7 @@ extern std::atomic<int> g_sk_target_ctas, g_sk_prefetch_rows, g_mega_dbg, g_mega
 using namespace ftcf;
 
 extern "C" const char* ftcf_last_error(void) { return g_err; }
-extern "C" int ftcf_abi_version(void) { return 1; }
+extern "C" int ftcf_abi_version(void) { return 2; }
 extern "C" long long ftcf_launch_count(void) { return g_launch_count.load(); }
 
 extern "C" int ftcf_set_tunable(const char* name, int value)

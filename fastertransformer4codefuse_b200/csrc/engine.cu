@@ -166,7 +166,7 @@ struct ftcf_gptneox {
     ncclComm_t comm = nullptr;
 
     // options
-    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_mega = 1;
+    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_mega = 0;   // mega: persistent decode-step kernel (decode_mega.cu), experimental -- measured slower than the graph (profiles/)
 
     // request-sized buffers (grow only)
     DevBuf kv, x, x2, n1, n2, qkv, qbuf, ctx, attn, inter, ffn, logits, logits_local, logits_gather, samp_ws, small, mmha_part,
@@ -267,6 +267,43 @@ int run_layer(ftcf_gptneox* e, int l, int m, AttnFn&& attn_fn)
     return FTCF_OK;
 }
 
+// Tiled weight copies + per-layer pointer table of the persistent decode-step kernel (decode_mega.cuh): one contiguous bulk
+// copy per ring stage.  Built on first use (option "mega" = 1); costs a second copy of the layer weights and the LM head.
+int mega_prepare(ftcf_gptneox* e)
+{
+    if (e->mega_weights) return FTCF_OK;
+    const ftcf_gptneox_config& c = e->cfg;
+    const int L = c.layer_num;
+    if (!(e->t == 1 && c.use_gptj_residual != 0 &&
+          mega_supported(1, e->h, e->hl, e->inter_l, c.size_per_head, c.rotary_embedding_dim, c.int8_mode == 1, e->t, true)))
+        return FTCF_OK;   // not applicable: the graph of per-operator kernels runs instead
+    const int gk[4] = {e->h, e->hl, e->h, e->inter_l};
+    const int gn[4] = {3 * e->hl, e->h, e->inter_l, e->h};
+    const int wsz = c.int8_mode == 1 ? 1 : 2;
+    std::vector<mg::LayerDev> ld(L);
+    for (int l = 0; l < L; ++l) {
+        const LayerW& lw = e->layers[l];
+        for (int kind = 0; kind < 4; ++kind) {
+            ld[l].scale[kind] = lw.scale[kind];
+            e->owned.emplace_back();
+            FTCF_TRY(e->owned.back().ensure(mega_tiled_bytes(gn[kind], gk[kind] * wsz)));
+            FTCF_TRY(mega_retile(lw.w[kind], e->owned.back().p, gn[kind], gk[kind] * wsz, e->stream));
+            ld[l].w[kind] = e->owned.back().p;
+        }
+        ld[l].ln1_g = lw.ln1_g; ld[l].ln1_b = lw.ln1_b; ld[l].ln2_g = lw.ln2_g; ld[l].ln2_b = lw.ln2_b;
+        ld[l].qkv_b = lw.qkv_b; ld[l].ffn1_b = lw.ffn1_b; ld[l].res_b = lw.ffn2_b;
+    }
+    FTCF_TRY(e->layer_dev.ensure(sizeof(mg::LayerDev) * L));
+    FTCF_CUDA_CHECK(cudaMemcpyAsync(e->layer_dev.p, ld.data(), sizeof(mg::LayerDev) * L, cudaMemcpyHostToDevice, e->stream));
+    e->owned.emplace_back();
+    FTCF_TRY(e->owned.back().ensure(mega_tiled_bytes(e->Vp, e->h * 2)));
+    FTCF_TRY(mega_retile(e->lm_head, e->owned.back().p, e->Vp, e->h * 2, e->stream));
+    e->lm_head_tiled = e->owned.back().p;
+    FTCF_CUDA_CHECK(cudaStreamSynchronize(e->stream));   // ld lives on this stack frame
+    e->mega_weights = true;
+    return FTCF_OK;
+}
+
 size_t kv_layer_elems(const ftcf_gptneox* e, int B, int max_len) { return (size_t)B * e->Hl * max_len * e->cfg.size_per_head; }
 
 }  // namespace
@@ -348,7 +385,8 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
                     std::vector<int8_t> hq(elems);
                     std::vector<uint8_t> ho(elems);
                     if (cudaMemcpy(hq.data(), q, elems, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("create: D2H of int8 weight failed"); status = FTCF_ERR_CUDA; break; }
-                    ftcf_int8_plain_to_b200_host(hq.data(), gk[kind], gn[kind], ho.data());
+                    if (c.int8_layout == 2) ftcf_int8_ampere_to_b200_host(hq.data(), gk[kind], gn[kind], ho.data());   // reference-made *.q.bin
+                    else ftcf_int8_plain_to_b200_host(hq.data(), gk[kind], gn[kind], ho.data());
                     e->owned.emplace_back();
                     status = e->owned.back().ensure(elems);
                     if (status == FTCF_OK && cudaMemcpy(e->owned.back().p, ho.data(), elems, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("create: H2D failed"); status = FTCF_ERR_CUDA; }
@@ -379,40 +417,8 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
             e->lm_head = e->lm_pad.as<__half>();
         }
     }
-    if (status == FTCF_OK) {
-        // per-layer pointer table of the persistent decode-step kernel, which streams the weights from a TILED copy
-        // (one contiguous bulk copy per ring stage, decode_mega.cuh)
-        std::vector<mg::LayerDev> ld(L);
-        const int wsz = c.int8_mode == 1 ? 1 : 2;
-        e->mega_weights = e->opt_mega != 0 && t == 1 && c.use_gptj_residual != 0 &&
-                          mega_supported(1, e->h, e->hl, e->inter_l, c.size_per_head, c.rotary_embedding_dim, c.int8_mode == 1, t, true);
-        for (int l = 0; l < L && status == FTCF_OK; ++l) {
-            const LayerW& lw = e->layers[l];
-            for (int kind = 0; kind < 4 && status == FTCF_OK; ++kind) {
-                ld[l].w[kind] = nullptr;
-                ld[l].scale[kind] = lw.scale[kind];
-                if (!e->mega_weights) continue;
-                e->owned.emplace_back();
-                status = e->owned.back().ensure(mega_tiled_bytes(gn[kind], gk[kind] * wsz));
-                if (status == FTCF_OK) status = mega_retile(lw.w[kind], e->owned.back().p, gn[kind], gk[kind] * wsz, e->stream);
-                ld[l].w[kind] = e->owned.back().p;
-            }
-            ld[l].ln1_g = lw.ln1_g; ld[l].ln1_b = lw.ln1_b; ld[l].ln2_g = lw.ln2_g; ld[l].ln2_b = lw.ln2_b;
-            ld[l].qkv_b = lw.qkv_b; ld[l].ffn1_b = lw.ffn1_b; ld[l].res_b = lw.ffn2_b;
-        }
-        status = e->layer_dev.ensure(sizeof(mg::LayerDev) * L);
-        if (status == FTCF_OK && cudaMemcpy(e->layer_dev.p, ld.data(), sizeof(mg::LayerDev) * L, cudaMemcpyHostToDevice) != cudaSuccess) {
-            set_error("create: upload of the layer table failed");
-            status = FTCF_ERR_CUDA;
-        }
-        if (status == FTCF_OK) status = e->gbar.ensure(256);
-        if (status == FTCF_OK && e->mega_weights) {
-            e->owned.emplace_back();
-            status = e->owned.back().ensure(mega_tiled_bytes(e->Vp, e->h * 2));
-            if (status == FTCF_OK) status = mega_retile(e->lm_head, e->owned.back().p, e->Vp, e->h * 2, e->stream);
-            e->lm_head_tiled = e->owned.back().p;
-        }
-    }
+    if (status == FTCF_OK) status = e->gbar.ensure(256);
+    if (status == FTCF_OK && e->opt_mega != 0) status = mega_prepare(e);
     if (status == FTCF_OK && t > 1) {
         if (!nccl_unique_id) { set_error("create: tensor_para_size %d needs an NCCL unique id", t); status = FTCF_ERR_INVALID; }
         if (status == FTCF_OK) status = nccl_load();
@@ -467,7 +473,10 @@ extern "C" int ftcf_gptneox_set_option(ftcf_gptneox* e, const char* name, int va
     else if (n == "gemm_impl") e->opt_gemm_impl = value;
     else if (n == "step_timing") e->opt_step_timing = value;
     else if (n == "two_branch") e->opt_two_branch = value;
-    else if (n == "mega") e->opt_mega = value;
+    else if (n == "mega") {
+        e->opt_mega = value;
+        if (value != 0) FTCF_TRY(mega_prepare(e));
+    }
     else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_option: unknown option %s", name);
     if (e->graph_exec) {   // anything captured may be stale
         cudaGraphExecDestroy(e->graph_exec);
@@ -565,6 +574,7 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     const int B = r.batch, S = r.max_input_len, out_len = r.output_len;
     FTCF_REQUIRE(B > 0 && S >= 1 && out_len >= 1, FTCF_ERR_INVALID, "forward: batch %d, input length %d, output_len %d", B, S, out_len);
     FTCF_REQUIRE(r.input_ids && r.input_lengths && r.output_ids && r.sequence_lengths, FTCF_ERR_INVALID, "forward: null tensor");
+    FTCF_REQUIRE(r.beam_width <= 1, FTCF_ERR_UNSUPPORTED, "forward: beam_width %d (beam search) is not implemented yet", r.beam_width);
     const int max_len = S + out_len;
     cudaStream_t st = e->stream;
     FTCF_CUDA_CHECK(cudaEventRecord(e->caller_ev, e->caller_stream));   // inputs were produced on the caller's stream

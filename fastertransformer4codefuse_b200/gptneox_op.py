@@ -131,7 +131,7 @@ class GptNeoXOp:
 
         rq = capi.GptNeoXRequest()
         rq.input_ids, rq.input_lengths = input_ids.data_ptr(), input_lengths.data_ptr()
-        rq.batch, rq.max_input_len, rq.output_len = B, S, int(output_len)
+        rq.batch, rq.max_input_len, rq.output_len, rq.beam_width = B, S, int(output_len), bw
         rq.top_k_host, rq.n_top_k = host(top_k, torch.int32)
         rq.top_p_host, rq.n_top_p = host(top_p, torch.float32)
         rq.temperature_host, rq.n_temperature = host(temperature, torch.float32)

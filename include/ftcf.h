@@ -197,7 +197,7 @@ typedef struct {
     int32_t int8_mode;            /* 0: fp16 weights, 1: weight-only int8                                    */
     int32_t use_gptj_residual;    /* 1: parallel residual                                                    */
     float layernorm_eps;          /* 1e-5 (models/gptneox/GptNeoX.h:42-43)                                   */
-    int32_t int8_layout;          /* 0: B200 layout (ours), 1: plain int8 [k,n] (re-laid out on the device)  */
+    int32_t int8_layout;          /* 0: B200 layout (ours), 1: plain int8 [k,n], 2: the reference's sm80 *.q.bin layout (1, 2: re-laid out at load) */
 } ftcf_gptneox_config;
 
 /* weights: 12*L+4 fp16 device pointers in GptNeoXOp order (th_op/gptneox/GptNeoXOp.h:121-174); int8_weights and
@@ -215,6 +215,7 @@ typedef struct {
     const int32_t* input_ids;       /* device [B, S]                                                         */
     const int32_t* input_lengths;   /* device [B]                                                            */
     int32_t batch, max_input_len, output_len;
+    int32_t beam_width;             /* 0 or 1: sampling; > 1: beam search (see ftcf_gptneox_forward)          */
     /* sampling arguments on the HOST, each either NULL, 1 element or B elements (n_* gives the count)       */
     const int32_t* top_k_host;  int32_t n_top_k;
     const float* top_p_host;    int32_t n_top_p;

@@ -184,3 +184,35 @@ def test_argument_errors_raise(cuda):
         op.forward(ids32, torch.tensor([9], dtype=torch.int32, device=cuda), 4)      # length > max_input_length
     with pytest.raises(RuntimeError):
         op.forward(ids32, torch.tensor([4], dtype=torch.int32, device=cuda), 4, 3)   # beam search not there yet
+
+
+def test_pybind_shim_runs_the_reference_call(cuda):
+    """libth_gptneox.GptNeoXOp (the compiled shim a user of codefuse_example.py loads) against the oracle: positional
+    arguments exactly as codefuse_example.py:533-536 (constructor) and :575-589 (forward)."""
+    import sys
+    from fastertransformer4codefuse_b200 import capi
+    if capi.LIB_DIR not in sys.path:
+        sys.path.append(capi.LIB_DIR)
+    import libth_gptneox
+    cfg = tiny_cfg()
+    rw = W.make_synthetic(cfg, 1, 0, 1, "cpu", seed=5, keep_plain=True)
+    ref = oracle_from_rank_weights(cfg, [rw], 1)
+    w, q, s = to_cuda_lists(rw, cuda)
+    op = libth_gptneox.GptNeoXOp(None, 0, cfg.head_num, cfg.size_per_head, cfg.inter_size, cfg.layer_num, cfg.vocab_size,
+                                 cfg.rotary_embedding_dim, cfg.start_id, cfg.end_id, 1, 1, 1, 1024, cfg.use_gptj_residual, w, q, s)
+    lens = [9, 14]
+    ids = _prompts(2, 14, cfg.vocab_size, lens)
+    seen = []
+    kw = dict(top_k=[4], top_p=[0.9], temperature=[0.7], repetition_penalty=[1.1], random_seed=[7])
+    res = op.forward(torch.from_numpy(ids).to(cuda), torch.tensor(lens, dtype=torch.int32, device=cuda), 8, 1,
+                     torch.tensor(kw["top_k"], dtype=torch.int32), torch.tensor(kw["top_p"]), None, torch.tensor(kw["temperature"]), None,
+                     torch.tensor(kw["repetition_penalty"]), torch.tensor(kw["random_seed"], dtype=torch.int64), None, None, 1, seen.append)
+    exp = ref.forward(ids, lens, 8, return_cum_log_probs=1, **kw)
+    assert len(res) == 3 and res[0].shape == (2, 1, 22) and res[0].dtype == torch.int32
+    assert np.array_equal(res[0].cpu().numpy(), exp["output_ids"])
+    assert np.array_equal(res[1].cpu().numpy(), exp["sequence_lengths"])
+    np.testing.assert_allclose(res[2].cpu().numpy(), exp["cum_log_probs"], rtol=2e-2, atol=2e-2)
+    assert len(seen) >= 1 and set(seen[0]) == {"last_tokens", "idxs"} and len(seen[0]["last_tokens"]) == 2
+    with pytest.raises(RuntimeError):
+        op.forward(torch.from_numpy(ids), torch.tensor(lens, dtype=torch.int32, device=cuda), 8, 1, None, None, None, None, None,
+                   None, None, None, None, 0, None)     # CPU input_ids
