@@ -46,6 +46,11 @@ class PrefetchHint(C.Structure):
     _fields_ = [("w", C.c_void_p), ("n", C.c_int32), ("row_bytes", C.c_int32)]
 
 
+class LnPrologue(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("add_ffn", C.c_void_p), ("add_attn", C.c_void_p), ("add_bias", C.c_void_p),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("x_out", C.c_void_p), ("eps", C.c_float)]
+
+
 class GptNeoXConfig(C.Structure):
     _fields_ = [
         ("head_num", C.c_int32), ("size_per_head", C.c_int32), ("inter_size", C.c_int32), ("layer_num", C.c_int32),
@@ -87,6 +92,8 @@ SIGNATURES = {
     "ftcf_device_check": (C.c_int, []),
     "ftcf_launch_count": (C.c_longlong, []),
     "ftcf_set_tunable": (C.c_int, [C.c_char_p, C.c_int]),
+    "ftcf_debug_trace_start": (C.c_int, [C.c_uint]),
+    "ftcf_debug_trace_stop": (C.c_int, [C.c_void_p, C.c_uint, C.POINTER(C.c_uint)]),
     "ftcf_symmetric_quantize_int8_host": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,
                                                     C.c_void_p, C.c_void_p]),
     "ftcf_int8_plain_to_b200_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
@@ -99,6 +106,10 @@ SIGNATURES = {
                                      C.c_int, C.c_int, C.POINTER(PrefetchHint), C.c_void_p]),
     "ftcf_gemm_f16_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.POINTER(PrefetchHint), C.c_void_p]),
+    "ftcf_gemm_w8a16_ln": (C.c_int, [C.POINTER(LnPrologue), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_void_p]),
+    "ftcf_gemm_f16_ln": (C.c_int, [C.POINTER(LnPrologue), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_void_p]),
     "ftcf_transpose_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ftcf_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "ftcf_add_bias_residual_layernorm": (C.c_int, [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),

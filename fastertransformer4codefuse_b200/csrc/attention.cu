@@ -25,7 +25,9 @@
 namespace ftcf {
 
 constexpr int MMHA_THREADS = 128;
-constexpr int MMHA_MAX_CHUNK = 4096;   // keys per split (fp32 scores kept in shared memory)
+constexpr int MMHA_MAX_CHUNK = 4096;
+std::atomic<int> g_mmha_prefetch{0};     // tunable "mmha_prefetch": L2 prefetch of the split's cache rows before the dependency wait
+std::atomic<int> g_mmha_pdl{0};          // tunable "mmha_pdl": launch the decode attention with programmatic dependent launch   // keys per split (fp32 scores kept in shared memory)
 
 __device__ __forceinline__ float rotary_angle(int pos, int i, int rot)
 {
@@ -46,6 +48,7 @@ __device__ __forceinline__ __half rotary_neox(__half xd, __half xpartner, int d,
 
 struct MmhaP {
     ftcf_mmha_params p;
+    int prefetch;
 };
 
 template <int DH>
@@ -54,7 +57,8 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
     const ftcf_mmha_params& p = params.p;
     constexpr int LPR = DH / 8;               // lanes per cache row (16 bytes each)
     constexpr int NG = MMHA_THREADS / LPR;    // row groups per CTA
-    constexpr int UNR = 4;
+    constexpr int UNR = 4;                    // rows per group per block, all in flight at once
+    constexpr int BLK = NG * UNR;             // keys per block (32 at dh = 128)
 
     __shared__ float s_scores[MMHA_MAX_CHUNK];
     __shared__ float s_out[NG][DH];
@@ -66,6 +70,11 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
 
     const int h = blockIdx.x, b = blockIdx.y, split = blockIdx.z;
     const int H = p.heads, tid = threadIdx.x;
+    const unsigned long long trc_t0 = trc_now(threadIdx.x == 0);
+    pdl_launch_dependents();                  // the O-projection GEMM may start streaming its weights now
+    // Everything read before pdl_wait() is constant for the whole decode step: the request state (lengths, finished flags: last
+    // written by the previous step's sampling kernels, which are ordinary launches and so completed before this step began)
+    // and cache rows of earlier positions.
     if (p.finished != nullptr && p.finished[b]) return;
 
     const int tlen = p.seq_len[b];
@@ -80,6 +89,21 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
     const __half* bias = static_cast<const __half*>(p.qkv_bias);
     __half* kc = static_cast<__half*>(p.k_cache) + ((size_t)b * H + h) * (size_t)p.max_len * DH;
     __half* vc = static_cast<__half*>(p.v_cache) + ((size_t)b * H + h) * (size_t)p.max_len * DH;
+    const int li = tid % LPR, gi = tid / LPR;
+
+    // ---- L2 prefetch of this split's cached K and V rows, issued BEFORE the dependency wait: the cache does not depend on the
+    // QKV GEMM that is still running, so the DRAM latency of the rows hides behind that kernel's tail and the loads after the
+    // wait are L2 hits.  (Keeping the rows in registers instead was measured slower: at 128 registers x 256 threads only two
+    // CTAs fit per SM next to the GEMM CTAs and the grid ran in waves.)
+    for (int pos = start + (tid >> 1); pos < end && params.prefetch; pos += MMHA_THREADS / 2) {
+        if (pos == tlen || (pos >= in_len && pos < max_in)) continue;
+        const __half* src = ((tid & 1) ? vc : kc) + (size_t)pos * DH;
+#pragma unroll
+        for (int c = 0; c < DH * 2; c += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(src) + c));
+    }
+
+    pdl_wait();                               // qkv of this layer is complete and visible
+    const unsigned long long trc_t1 = trc_now(threadIdx.x == 0);
 
     // ---- q (all splits), k / v (owner split): bias, rotary, append to the cache
     for (int d = tid; d < DH; d += MMHA_THREADS) {
@@ -116,7 +140,6 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
     }
     __syncthreads();
 
-    const int li = tid % LPR, gi = tid / LPR;
     float q[8];
     {
         const uint4 qv = *reinterpret_cast<const uint4*>(&s_q[li * 8]);
@@ -130,7 +153,7 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
     }
 
     // ---- scores
-    for (int base = start; base < end; base += NG * UNR) {
+    for (int base = start; base < end; base += BLK) {
         uint4 kv[UNR];
         bool valid[UNR];
 #pragma unroll
@@ -180,7 +203,7 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int base = start; base < end; base += NG * UNR) {
+    for (int base = start; base < end; base += BLK) {
         uint4 vv[UNR];
         float pr[UNR];
 #pragma unroll
@@ -216,6 +239,7 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
             for (int g = 0; g < NG; ++g) o += s_out[g][d];
             ctx[d] = __float2half_rn(o * (1.f / (sum + 1e-6f)));
         }
+        if (tid == 0) trc_emit(TRC_MMHA, trc_t0, trc_t1, trc_t1, end - start, 0);
         return;
     }
 
@@ -238,7 +262,11 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
         s_flag = (old == p.splits - 1);
     }
     __syncthreads();
-    if (!s_flag) return;
+    if (!s_flag) {
+        if (tid == 0) trc_emit(TRC_MMHA, trc_t0, trc_t1, trc_t1, end - start, 0);
+        return;
+    }
+    const unsigned long long trc_t2 = trc_now(threadIdx.x == 0);
     __threadfence();
     const float* all = p.partial + (size_t)(b * H + h) * p.splits * (DH + 2);
     float M = -INFINITY;
@@ -253,8 +281,13 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
         }
         ctx[d] = __float2half_rn(O * (1.f / (L + 1e-6f)));
     }
-    if (tid == 0) p.counters[b * H + h] = 0;
+    if (tid == 0) {
+        p.counters[b * H + h] = 0;
+        trc_emit(TRC_MMHA, trc_t0, trc_t1, trc_t2, end - start, 1);
+    }
 }
+
+FTCF_TRACE_INSTALLER(trace_install_attention)
 
 // ---------------------------------------------------------------- prefill: bias + rotary + scatter
 template <int DH>
@@ -418,14 +451,19 @@ extern "C" int ftcf_mmha_decode(const ftcf_mmha_params* p, void* stream)
     FTCF_REQUIRE(p->splits == 1 || (p->partial != nullptr && p->counters != nullptr), FTCF_ERR_INVALID,
                  "mmha: split-KV needs scratch");
     FTCF_REQUIRE(p->rotary_dim % 2 == 0 && p->rotary_dim <= p->dh, FTCF_ERR_INVALID, "mmha: rotary_dim %d", p->rotary_dim);
-    MmhaP mp{*p};
+    MmhaP mp{*p, g_mmha_prefetch.load()};
     const dim3 grid(p->heads, p->batch, p->splits);
+    cudaError_t lerr = cudaSuccess;
+    const int pdl_saved = g_pdl_enabled.load();
+    if (!g_mmha_pdl.load()) g_pdl_enabled.store(0);
     switch (p->dh) {
-        case 64: mmha_decode_kernel<64><<<grid, MMHA_THREADS, 0, as_stream(stream)>>>(mp); break;
-        case 128: mmha_decode_kernel<128><<<grid, MMHA_THREADS, 0, as_stream(stream)>>>(mp); break;
-        case 256: mmha_decode_kernel<256><<<grid, MMHA_THREADS, 0, as_stream(stream)>>>(mp); break;
+        case 64: lerr = launch_pdl(mmha_decode_kernel<64>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
+        case 128: lerr = launch_pdl(mmha_decode_kernel<128>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
+        case 256: lerr = launch_pdl(mmha_decode_kernel<256>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
         default: FTCF_REQUIRE(false, FTCF_ERR_UNSUPPORTED, "mmha: size_per_head %d (supported: 64, 128, 256)", p->dh);
     }
+    g_pdl_enabled.store(pdl_saved);
+    FTCF_REQUIRE(lerr == cudaSuccess, FTCF_ERR_CUDA, "mmha launch failed: %s", cudaGetErrorString(lerr));
     FTCF_LAUNCH_CHECK();
     return FTCF_OK;
 }

@@ -29,12 +29,17 @@ int gemm_w8a16_skinny(const void* x, const uint8_t* w_nk, const void* scale, con
                       int act, const ftcf_prefetch_hint* next, cudaStream_t st);
 int gemm_f16_skinny(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
                     int out_f32, const ftcf_prefetch_hint* next, cudaStream_t st);
+int gemm_w8a16_skinny_ln(const ftcf_ln_prologue& pro, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n, int k,
+                         int act, cudaStream_t st);
+int gemm_f16_skinny_ln(const ftcf_ln_prologue& pro, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
+                       int out_f32, cudaStream_t st);
 int gemm_w8a16_tcgen05(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n, int k,
                        int act, cudaStream_t st);
 int gemm_f16_tcgen05(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
                      int out_f32, cudaStream_t st);
 bool gemm_tcgen05_supported(int m, int n, int k, int elem_bytes);
-extern std::atomic<int> g_sk_target_ctas, g_sk_prefetch_rows, g_mega_dbg, g_mega_ns, g_mega_inflight;
+extern std::atomic<int> g_mmha_pdl, g_mmha_prefetch, g_sk_carveout;
+extern std::atomic<int> g_sk_target_ctas, g_sk_prefetch_rows, g_sk_pf_ahead, g_mega_dbg, g_mega_ns, g_mega_inflight;
 
 }  // namespace ftcf
 
@@ -51,11 +56,64 @@ extern "C" int ftcf_set_tunable(const char* name, int value)
     if (n == "pdl") g_pdl_enabled.store(value);
     else if (n == "skinny_target_ctas") { FTCF_REQUIRE(value >= 1, FTCF_ERR_INVALID, "skinny_target_ctas %d", value); g_sk_target_ctas.store(value); }
     else if (n == "skinny_prefetch_rows") { FTCF_REQUIRE(value >= 0, FTCF_ERR_INVALID, "skinny_prefetch_rows %d", value); g_sk_prefetch_rows.store(value); }
+    else if (n == "skinny_pf_ahead") g_sk_pf_ahead.store(value);
+    else if (n == "mmha_pdl") g_mmha_pdl.store(value);
+    else if (n == "mmha_prefetch") g_mmha_prefetch.store(value);
+    else if (n == "skinny_carveout") g_sk_carveout.store(value);
     else if (n == "mega_dbg") g_mega_dbg.store(value);
     else if (n == "mega_ns") g_mega_ns.store(value);
     else if (n == "mega_inflight") g_mega_inflight.store(value);
     else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_tunable: unknown tunable %s", name);
     return FTCF_OK;
+}
+
+// ---------------------------------------------------------------- per-CTA timeline (debug)
+namespace ftcf {
+int trace_install_gemm_skinny(TraceRec*, unsigned*, unsigned);
+int trace_install_attention(TraceRec*, unsigned*, unsigned);
+int trace_install_norm_residual(TraceRec*, unsigned*, unsigned);
+int trace_install_sampling(TraceRec*, unsigned*, unsigned);
+}  // namespace ftcf
+static TraceRec* g_trace_dev = nullptr;
+static unsigned* g_trace_cnt_dev = nullptr;
+static unsigned g_trace_cap = 0;
+static int trace_install_all(TraceRec* buf, unsigned* cnt, unsigned cap)
+{
+    int rc = trace_install_gemm_skinny(buf, cnt, cap);
+    if (rc == FTCF_OK) rc = trace_install_attention(buf, cnt, cap);
+    if (rc == FTCF_OK) rc = trace_install_norm_residual(buf, cnt, cap);
+    if (rc == FTCF_OK) rc = trace_install_sampling(buf, cnt, cap);
+    return rc;
+}
+
+extern "C" int ftcf_debug_trace_start(unsigned capacity)
+{
+    FTCF_CUDA_CHECK(cudaDeviceSynchronize());
+    if (g_trace_dev == nullptr || g_trace_cap < capacity) {
+        if (g_trace_dev) cudaFree(g_trace_dev);
+        if (g_trace_cnt_dev) cudaFree(g_trace_cnt_dev);
+        g_trace_dev = nullptr;
+        FTCF_CUDA_CHECK(cudaMalloc(&g_trace_dev, (size_t)capacity * sizeof(TraceRec)));
+        FTCF_CUDA_CHECK(cudaMalloc(&g_trace_cnt_dev, sizeof(unsigned)));
+        g_trace_cap = capacity;
+    }
+    FTCF_CUDA_CHECK(cudaMemset(g_trace_cnt_dev, 0, sizeof(unsigned)));
+    return trace_install_all(g_trace_dev, g_trace_cnt_dev, g_trace_cap);
+}
+
+// stops tracing and copies up to max_records records (sizeof == 56) to host memory; returns the count through *n
+extern "C" int ftcf_debug_trace_stop(void* out_host, unsigned max_records, unsigned* n)
+{
+    FTCF_REQUIRE(n != nullptr, FTCF_ERR_INVALID, "trace_stop: null");
+    *n = 0;
+    if (g_trace_dev == nullptr) return FTCF_OK;
+    FTCF_CUDA_CHECK(cudaDeviceSynchronize());
+    unsigned cnt = 0;
+    FTCF_CUDA_CHECK(cudaMemcpy(&cnt, g_trace_cnt_dev, sizeof(cnt), cudaMemcpyDeviceToHost));
+    cnt = std::min(cnt, std::min(g_trace_cap, max_records));
+    if (out_host != nullptr && cnt > 0) FTCF_CUDA_CHECK(cudaMemcpy(out_host, g_trace_dev, (size_t)cnt * sizeof(TraceRec), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    return trace_install_all(nullptr, nullptr, 0);
 }
 
 extern "C" int ftcf_device_check(void)
@@ -91,6 +149,25 @@ extern "C" int ftcf_gemm_w8a16(const void* x, const uint8_t* w_nk, const void* s
                                int k, int act, int impl, void* stream)
 {
     return ftcf_gemm_w8a16_ex(x, w_nk, scale, bias, y, m, n, k, act, impl, nullptr, stream);
+}
+
+extern "C" int ftcf_gemm_w8a16_ln(const ftcf_ln_prologue* pro, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m,
+                                  int n, int k, int act, void* stream)
+{
+    FTCF_REQUIRE(pro && w_nk && scale && y, FTCF_ERR_INVALID, "gemm_w8a16_ln: null operand");
+    FTCF_REQUIRE(act == 0 || act == 1, FTCF_ERR_INVALID, "gemm_w8a16_ln: act %d", act);
+    FTCF_REQUIRE(pro->x_out == nullptr || pro->x_out != pro->x, FTCF_ERR_INVALID, "gemm_w8a16_ln: x_out must not alias x");
+    return gemm_w8a16_skinny_ln(*pro, w_nk, scale, bias, y, m, n, k, act, as_stream(stream));
+}
+
+extern "C" int ftcf_gemm_f16_ln(const ftcf_ln_prologue* pro, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy,
+                                int act, int out_f32, void* stream)
+{
+    FTCF_REQUIRE(pro && w_nk && y, FTCF_ERR_INVALID, "gemm_f16_ln: null operand");
+    FTCF_REQUIRE(act == 0 || act == 1, FTCF_ERR_INVALID, "gemm_f16_ln: act %d", act);
+    FTCF_REQUIRE(ldy >= n, FTCF_ERR_INVALID, "gemm_f16_ln: ldy %d < n %d", ldy, n);
+    FTCF_REQUIRE(pro->x_out == nullptr || pro->x_out != pro->x, FTCF_ERR_INVALID, "gemm_f16_ln: x_out must not alias x");
+    return gemm_f16_skinny_ln(*pro, w_nk, bias, y, m, n, k, ldy, act, out_f32, as_stream(stream));
 }
 
 extern "C" int ftcf_gemm_f16_ex(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,

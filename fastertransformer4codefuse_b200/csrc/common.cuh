@@ -43,6 +43,51 @@ extern std::atomic<long long> g_launch_count;   // kernels launched by this libr
         }                                                                                             \
     } while (0)
 
+// ---------------------------------------------------------------- per-CTA timeline (debug; off unless ftcf_debug_trace_start)
+// Every instrumented kernel appends one record per CTA: globaltimer stamps of its start, the end of its dependency wait, its
+// first useful work and its end.  Device globals are per translation unit (no -rdc), so each .cu that emits records defines an
+// installer with FTCF_TRACE_INSTALLER(name) and capi.cu calls them all.
+struct TraceRec {
+    unsigned long long t0, t1, t2, t3;
+    int kind, cta, ncta, a, b, pad;
+};
+enum { TRC_GEMM_W8 = 1, TRC_GEMM_F16 = 2, TRC_MMHA = 10, TRC_LN = 20, TRC_RESIDUAL = 21, TRC_EMBED = 22, TRC_SAMPLING = 30 };
+#ifdef __CUDACC__
+static __device__ TraceRec* g_trc_buf = nullptr;
+static __device__ unsigned* g_trc_cnt = nullptr;
+static __device__ unsigned g_trc_cap = 0;
+// `who`: only the one thread that will emit the record reads the timer, and only while a trace buffer is installed
+// (%globaltimer reads are slow; 256 threads x 3 reads per CTA cost several per cent of a decode step)
+__device__ __forceinline__ unsigned long long trc_now(bool who = true)
+{
+    if (!who || g_trc_buf == nullptr) return 0;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trc_emit(int kind, unsigned long long t0, unsigned long long t1, unsigned long long t2, int a, int b)
+{
+    if (g_trc_buf == nullptr) return;
+    const unsigned i = atomicAdd(g_trc_cnt, 1u);
+    if (i >= g_trc_cap) return;
+    TraceRec r;
+    r.t0 = t0; r.t1 = t1; r.t2 = t2; r.t3 = trc_now();
+    r.kind = kind;
+    r.cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    r.ncta = gridDim.x * gridDim.y * gridDim.z;
+    r.a = a; r.b = b; r.pad = 0;
+    g_trc_buf[i] = r;
+}
+#define FTCF_TRACE_INSTALLER(name)                                                        \
+    int name(TraceRec* buf, unsigned* cnt, unsigned cap)                                  \
+    {                                                                                     \
+        FTCF_CUDA_CHECK(cudaMemcpyToSymbol(g_trc_buf, &buf, sizeof(buf)));                \
+        FTCF_CUDA_CHECK(cudaMemcpyToSymbol(g_trc_cnt, &cnt, sizeof(cnt)));                \
+        FTCF_CUDA_CHECK(cudaMemcpyToSymbol(g_trc_cap, &cap, sizeof(cap)));                \
+        return FTCF_OK;                                                                   \
+    }
+#endif
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // Programmatic dependent launch (PDL): the decode step is a chain of short HBM-bound kernels; with this attribute the next

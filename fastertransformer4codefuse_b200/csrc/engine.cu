@@ -15,6 +15,7 @@
 
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -166,11 +167,12 @@ struct ftcf_gptneox {
     ncclComm_t comm = nullptr;
 
     // options
-    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_mega = 0;   // mega: persistent decode-step kernel (decode_mega.cu), experimental -- measured slower than the graph (profiles/)
+    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_mega = 0;   // mega: persistent decode-step kernel (decode_mega.cu), experimental -- measured slower than the graph (profiles/)
 
     // request-sized buffers (grow only)
     DevBuf kv, x, x2, n1, n2, qkv, qbuf, ctx, attn, inter, ffn, logits, logits_local, logits_gather, samp_ws, small, mmha_part,
-        prompt_meta, lm_pad, layer_dev, ffn_part, att_part, gbar;
+        prompt_meta, lm_pad, layer_dev, ffn_part, att_part, gbar, attn_b, ffn_b;
+    bool fused_on = false;              // decode layers run with the residual + LayerNorm prologue fused into the QKV / FFN1 / LM-head GEMMs
     mg::Params mega{};                  // persistent decode-step kernel arguments of the current request
     bool mega_on = false, mega_weights = false;
     const void* lm_head_tiled = nullptr;
@@ -342,9 +344,19 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
     e->caller_stream = as_stream(stream);
     // Stream capture is not allowed on the legacy default stream, which is what torch hands over by default, so the
     // engine owns a stream and orders it after the caller's with an event at the start of every request.
-    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // The attention branch of a decode layer (QKV -> attention -> O) is a chain of three dependent, partly latency-bound
+    // kernels; the FFN branch is two big weight streams.  The main stream (attention branch) gets the highest priority so that
+    // its CTAs are placed first and the latency-bound part overlaps the FFN streaming instead of trailing it.
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (const char* pe = std::getenv("FTCF_STREAM_PRIO")) {   // experiment hook: 0 = no priorities, -1 = reversed
+        const int v = std::atoi(pe);
+        if (v == 0) prio_greatest = prio_least = 0;
+        if (v < 0) std::swap(prio_least, prio_greatest);
+    }
+    if (cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->caller_ev, cudaEventDisableTiming) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         set_error("create: cannot create the engine stream");
@@ -452,7 +464,7 @@ extern "C" void ftcf_gptneox_destroy(ftcf_gptneox* e)
     for (auto& b : e->owned) b.release();
     DevBuf* bufs[] = {&e->kv, &e->x, &e->x2, &e->n1, &e->n2, &e->qkv, &e->qbuf, &e->ctx, &e->attn, &e->inter, &e->ffn, &e->logits,
                       &e->logits_local, &e->logits_gather, &e->samp_ws, &e->small, &e->mmha_part, &e->prompt_meta, &e->lm_pad, &e->layer_dev,
-                      &e->ffn_part, &e->att_part, &e->gbar};
+                      &e->ffn_part, &e->att_part, &e->gbar, &e->attn_b, &e->ffn_b};
     for (DevBuf* b : bufs) b->release();
     if (e->host_flag) cudaFreeHost(e->host_flag);
     if (e->host_stage) cudaFreeHost(e->host_stage);
@@ -473,6 +485,7 @@ extern "C" int ftcf_gptneox_set_option(ftcf_gptneox* e, const char* name, int va
     else if (n == "gemm_impl") e->opt_gemm_impl = value;
     else if (n == "step_timing") e->opt_step_timing = value;
     else if (n == "two_branch") e->opt_two_branch = value;
+    else if (n == "fused_ln") e->opt_fused_ln = value;
     else if (n == "mega") {
         e->opt_mega = value;
         if (value != 0) FTCF_TRY(mega_prepare(e));
@@ -518,6 +531,76 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
         mp.out_ids = s.out_ids; mp.step = s.step; mp.seq_len = s.seq_len; mp.input_len = s.input_len; mp.pad_count = s.pad_count;
         mp.finished = s.finished; mp.att_cnt = s.counters;
         return mega_launch(mp, c.int8_mode == 1, st);
+    }
+    if (e->fused_on) {
+        // B <= 4, one GPU, parallel residual: the residual add of layer l-1 and the LayerNorms of layer l are the prologue of
+        // layer l's QKV and FFN1 GEMMs (ftcf_gemm_*_ln); the residual stream ping-pongs between x and x2 and the branch
+        // outputs between two (attn, ffn) pairs, so no kernel overwrites what a concurrently running one still reads.
+        __half* xb[2] = {e->x.as<__half>(), e->x2.as<__half>()};
+        __half* attn[2] = {e->attn.as<__half>(), e->attn_b.as<__half>()};
+        __half* ffn[2] = {e->ffn.as<__half>(), e->ffn_b.as<__half>()};
+        const int L = run_layers ? c.layer_num : 0;
+        const bool w8 = c.int8_mode == 1;
+        if (run_layers) {
+            const size_t total = (size_t)B * e->h / 8;
+            embedding_prev_token_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xb[0], e->wte, s.out_ids, s.step, B, e->h, c.vocab_size);
+            FTCF_LAUNCH_CHECK();
+        }
+        const size_t per_layer = kv_layer_elems(e, B, max_len);
+        auto prologue = [&](int l, const __half* g, const __half* b, bool store) {
+            ftcf_ln_prologue pro{};
+            pro.gamma = g; pro.beta = b; pro.eps = c.layernorm_eps;
+            if (l == 0) {
+                pro.x = xb[0];
+            } else {
+                pro.x = xb[(l - 1) & 1];
+                pro.add_ffn = ffn[(l - 1) & 1];
+                pro.add_attn = attn[(l - 1) & 1];
+                pro.add_bias = e->layers[l - 1].ffn2_b;   // (b_o + b_ffn2) / t, huggingface_convert.py:35-41,192-206
+                if (store) pro.x_out = xb[l & 1];
+            }
+            return pro;
+        };
+        for (int l = 0; l < L; ++l) {
+            const LayerW& lw = e->layers[l];
+            cudaStream_t sb = e->opt_two_branch ? e->side : st;
+            // The FFN branch is issued first: measured best (its two big weight streams take the SMs, the attention branch's
+            // shorter kernels fill in).  Issuing QKV first, or forking only after QKV, was 8-25 % slower per token.
+            if (e->opt_two_branch) {
+                FTCF_CUDA_CHECK(cudaEventRecord(e->ev_fork, st));
+                FTCF_CUDA_CHECK(cudaStreamWaitEvent(sb, e->ev_fork, 0));
+            }
+            const ftcf_ln_prologue p2 = prologue(l, lw.ln2_g, lw.ln2_b, false);
+            if (w8) {
+                FTCF_TRY(ftcf_gemm_w8a16_ln(&p2, static_cast<const uint8_t*>(lw.w[2]), lw.scale[2], lw.ffn1_b, e->inter.p, B, e->inter_l, e->h, 1, sb));
+                FTCF_TRY(ftcf_gemm_w8a16(e->inter.p, static_cast<const uint8_t*>(lw.w[3]), lw.scale[3], nullptr, ffn[l & 1], B, e->h, e->inter_l, 0, 1, sb));
+            } else {
+                FTCF_TRY(ftcf_gemm_f16_ln(&p2, lw.w[2], lw.ffn1_b, e->inter.p, B, e->inter_l, e->h, e->inter_l, 1, 0, sb));
+                FTCF_TRY(ftcf_gemm_f16(e->inter.p, lw.w[3], nullptr, ffn[l & 1], B, e->h, e->inter_l, e->h, 0, 0, 1, sb));
+            }
+            if (e->opt_two_branch) FTCF_CUDA_CHECK(cudaEventRecord(e->ev_join, sb));
+            const ftcf_ln_prologue p1 = prologue(l, lw.ln1_g, lw.ln1_b, true);
+            if (w8) FTCF_TRY(ftcf_gemm_w8a16_ln(&p1, static_cast<const uint8_t*>(lw.w[0]), lw.scale[0], nullptr, e->qkv.p, B, 3 * e->hl, e->h, 0, st));
+            else FTCF_TRY(ftcf_gemm_f16_ln(&p1, lw.w[0], nullptr, e->qkv.p, B, 3 * e->hl, e->h, 3 * e->hl, 0, 0, st));
+            ftcf_mmha_params mp{};
+            mp.qkv = e->qkv.p;
+            mp.qkv_bias = lw.qkv_b;
+            mp.k_cache = e->kv.as<__half>() + (size_t)(2 * l) * per_layer;
+            mp.v_cache = e->kv.as<__half>() + (size_t)(2 * l + 1) * per_layer;
+            mp.ctx = e->ctx.p;
+            mp.seq_len = s.seq_len; mp.input_len = s.input_len; mp.pad_count = s.pad_count; mp.finished = s.finished; mp.step = s.step;
+            mp.partial = e->mmha_part.as<float>(); mp.counters = s.counters;
+            mp.batch = B; mp.heads = e->Hl; mp.dh = dh; mp.rotary_dim = c.rotary_embedding_dim;
+            mp.max_len = max_len; mp.max_input_len = S; mp.splits = splits;
+            mp.inv_sqrt_dh = 1.f / std::sqrt((float)dh);
+            FTCF_TRY(ftcf_mmha_decode(&mp, st));
+            if (w8) FTCF_TRY(ftcf_gemm_w8a16(e->ctx.p, static_cast<const uint8_t*>(lw.w[1]), lw.scale[1], nullptr, attn[l & 1], B, e->h, e->hl, 0, 1, st));
+            else FTCF_TRY(ftcf_gemm_f16(e->ctx.p, lw.w[1], nullptr, attn[l & 1], B, e->h, e->hl, e->h, 0, 0, 1, st));
+            if (e->opt_two_branch) FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join, 0));
+        }
+        // final LayerNorm (on the last layer's residual sum) as the prologue of the LM head
+        const ftcf_ln_prologue pf = prologue(L, e->lnf_g, e->lnf_b, false);
+        return ftcf_gemm_f16_ln(&pf, e->lm_head, nullptr, e->logits.p, B, e->Vp, e->h, e->Vp, 0, 1, st);
     }
     if (run_layers) {
         const size_t total = (size_t)B * e->h / 8;
@@ -643,6 +726,11 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     FTCF_TRY(e->mmha_part.ensure((size_t)B * e->Hl * splits * (dh + 2) * 4 + 256));
     e->mega_on = e->opt_mega != 0 && e->mega_weights &&
                  mega_supported(B, e->h, e->hl, e->inter_l, dh, c.rotary_embedding_dim, c.int8_mode == 1, e->t, c.use_gptj_residual != 0);
+    e->fused_on = !e->mega_on && e->opt_fused_ln != 0 && B <= 4 && e->t == 1 && c.use_gptj_residual != 0 && e->h % 128 == 0 && e->h <= 16384;
+    if (e->fused_on) {
+        FTCF_TRY(e->attn_b.ensure((size_t)B * e->h * 2));
+        FTCF_TRY(e->ffn_b.ensure((size_t)B * e->h * 2));
+    }
     if (e->mega_on) {
         mg::Params& mp = e->mega;
         mp = mg::Params{};
@@ -798,9 +886,9 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     const bool want_trace = r.logits_trace != nullptr && r.logits_trace_steps > 0;
     const bool use_graph = e->opt_cuda_graph != 0 && out_len > 2 && !want_trace;
     char keybuf[256];
-    snprintf(keybuf, sizeof(keybuf), "B%d S%d M%d k%d t%d r%d p%d l%p s%p n%d/%d kv%p x%p sm%p lg%p", B, S, max_len, max_top_k, (int)any_temp,
+    snprintf(keybuf, sizeof(keybuf), "B%d S%d M%d k%d t%d r%d p%d l%p s%p n%d/%d kv%p x%p sm%p lg%p f%d", B, S, max_len, max_top_k, (int)any_temp,
              (int)any_rep, sp.want_probs, (const void*)sp.optional_last_tokens, (const void*)sp.stop_words, sp.n_last, sp.n_stop, e->kv.p, e->x.p,
-             e->small.p, e->logits.p);
+             e->small.p, e->logits.p, (int)e->fused_on);
     const std::string key(keybuf);
 
     int steps_done = 0;

@@ -40,6 +40,7 @@ __device__ __forceinline__ void u8x4_to_h2x2(uint32_t w, uint32_t& lo, uint32_t&
     asm("sub.f16x2 %0, %1, %2;" : "=r"(hi) : "r"(hi), "r"(magic));
 }
 
+__device__ __forceinline__ int cw_of(int warp) { return warp - 1; }   // consumer-warp index (warp 0 is the producer)
 __device__ __forceinline__ uint32_t u4_get(const uint4& v, int i)
 {
     return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
@@ -48,6 +49,8 @@ __device__ __forceinline__ uint32_t u4_get(const uint4& v, int i)
 // tunables (ftcf_set_tunable): how many CTAs one launch aims for (all of them co-resident, so HBM is shared evenly and the
 // next kernel's CTAs fit beside them) -- see launch_skinny.
 std::atomic<int> g_sk_target_ctas{296};
+std::atomic<int> g_sk_carveout{1};       // 1: ask for the maximum shared-memory carveout (3 CTAs per SM fit)
+std::atomic<int> g_sk_pf_ahead{0};       // stages (16 KB each) of its OWN stream a producer keeps prefetched in L2 beyond the shared-memory ring
 std::atomic<int> g_sk_prefetch_rows{0};  // rows of each NEXT-kernel CTA slice that a finishing CTA prefetches into L2; measured on B200: it does not pay (gcb_2.log), so 0 = off
 
 namespace sk {
@@ -60,6 +63,18 @@ constexpr int THREADS = 288;             // warp 0: TMA producer, warps 1..8: co
 using namespace tma;
 }  // namespace sk
 
+// Fused prologue of the decode layer (m <= 4 tokens): the CTA builds its own copy of the GEMM input in shared memory,
+//   r = ((add_ffn + add_attn) + add_bias) + x       (the PREVIOUS layer's parallel-residual add, add_residual_kernels.cu:116-176;
+//                                                    skipped when add_ffn == NULL)
+//   a = LayerNorm(r; gamma, beta)                   (layernorm_kernels.cu:158-286: fp32 statistics, half2 normalisation)
+// instead of reading what a residual kernel and a LayerNorm kernel wrote: two launches (and their kernel boundaries, ~5 us of
+// idle HBM each) leave the critical path of every layer.  Every CTA recomputes the same 10 KB row (L2 hits); CTA 0 stores r.
+struct SkPro {
+    const __half *x, *add_ffn, *add_attn, *add_bias, *gamma, *beta;
+    __half* x_out;
+    float eps;
+};
+
 // Pipelined skinny GEMM.  One CTA owns the contiguous feature rows [r0, r1) and all of k.
 //   producer      : one thread issues four TMA boxes (32 rows x 128 bytes, SWIZZLE_128B) per stage, 4 stages = 64 KB in flight
 //                   per CTA and no registers; it never waits for the producer KERNEL (weights are constants), so with PDL
@@ -68,11 +83,11 @@ using namespace tma;
 //                   128-byte swizzle), converts
 //                   u8 -> fp16 in registers and issues mma.sync.m16n8k16 against the token fragments (read through L1);
 //   end of a pass : the four k-step warps of a tile are summed through shared memory in a fixed order, epilogue, store.
-template <typename WT, int MT, int EPI>
+template <typename WT, int MT, int EPI, bool PRO = false>
 __global__ void __launch_bounds__(sk::THREADS, (MT <= 2 ? 2 : 1))
-gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __half* __restrict__ x, const __half* __restrict__ scale,
+gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, const __half* __restrict__ x, const __half* __restrict__ scale,
                    const __half* __restrict__ bias, void* __restrict__ y, int m, int n, int k, int ldy, int act, int rows_per_cta,
-                   const uint8_t* __restrict__ next_w, int next_n, int next_row_bytes, int next_rows_per_cta, int next_pf_rows)
+                   const uint8_t* __restrict__ next_w, int next_n, int next_row_bytes, int next_rows_per_cta, int next_pf_rows, int pf_ahead)
 {
     using namespace sk;
     constexpr int EPC = 16 / sizeof(WT);   // k-elements per 16-byte chunk
@@ -108,7 +123,20 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __half* __re
         // ================= producer =================
         if (lane == 0) {
             prefetch_map(&map_w);
+            // L2 prefetch window: while this CTA's consumers still wait for the previous kernel (PDL) -- and HBM would idle
+            // through the kernel boundary with only the 64 KB ring requested -- the producer keeps asking L2 for the stages
+            // that follow the ring, so the ring later refills at L2 latency.
             for (int i = 0; i < total; ++i) {
+                if (i == STAGES && pf_ahead > 0) {
+                    // the ring is full and this thread is about to block until the consumers start (they wait for the previous
+                    // kernel): one burst of L2 prefetches for the stages that follow the ring.  (A rolling window was measured
+                    // to cost steady-state bandwidth: every byte then crosses L2 twice.)
+                    for (int pf_i = STAGES; pf_i < min(total, STAGES + pf_ahead); ++pf_i) {
+                        const int ppass = pf_i / chunks, pkc = pf_i % chunks;
+                        const int pn = min(4, (row_bytes - pkc * CHUNK) / 128);
+                        for (int j = 0; j < pn; ++j) prefetch_2d(&map_w, (pkc * CHUNK + j * 128) / (int)sizeof(WT), r0 + ppass * ROWS);
+                    }
+                }
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
                 const int pass = i / chunks, kc = i % chunks;
@@ -138,12 +166,88 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __half* __re
     // ================= consumers =================
     const int cw = warp - 1, tile = cw >> 2, ks = cw & 3;
     const int g = lane >> 2, t = lane & 3;
-    pdl_wait();                              // x comes from the previous kernel; y may still be read by it
+    const bool trc_who = threadIdx.x == 32;
+    const unsigned long long trc_t0 = trc_now(trc_who);
+    pdl_wait();
+    const unsigned long long trc_t1 = trc_now(trc_who);
+    unsigned long long trc_t2 = 0;                              // x comes from the previous kernel; y may still be read by it
     const __half* xrow[MT];
+    if constexpr (PRO) {
+        // ---- fused residual + LayerNorm into shared memory (row pitch k + 8 halves: rows fall into different banks)
+        __half* xs = reinterpret_cast<__half*>(sk_smem + (size_t)STAGES * STAGE_BYTES);
+        const int pitch = k + 8, nvec = k >> 3, ct = threadIdx.x - 32;
+        float* pred = &red[0][0][0];
+        const bool writer = pro.x_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+        for (int b = 0; b < m; ++b) {
+            float s = 0.f, ss = 0.f;
+            for (int vi = ct; vi < nvec; vi += 256) {
+                uint4 v = *reinterpret_cast<const uint4*>(pro.x + (size_t)b * k + vi * 8);
+                if (pro.add_ffn != nullptr) {
+                    const uint4 fv = *reinterpret_cast<const uint4*>(pro.add_ffn + (size_t)b * k + vi * 8);
+                    const uint4 av = *reinterpret_cast<const uint4*>(pro.add_attn + (size_t)b * k + vi * 8);
+                    uint4 bv = make_uint4(0, 0, 0, 0);
+                    if (pro.add_bias != nullptr) bv = *reinterpret_cast<const uint4*>(pro.add_bias + vi * 8);
+                    __half2* xh = reinterpret_cast<__half2*>(&v);
+                    const __half2* fh = reinterpret_cast<const __half2*>(&fv);
+                    const __half2* ah = reinterpret_cast<const __half2*>(&av);
+                    const __half2* bh = reinterpret_cast<const __half2*>(&bv);
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-        const int tok = min(m0 + mt * 8 + g, m - 1);
-        xrow[mt] = x + (size_t)tok * k + ks * KSTEP + t * 2 * EPC;
+                    for (int j = 0; j < 4; ++j) {
+                        __half2 r = __hadd2(fh[j], ah[j]);
+                        if (pro.add_bias != nullptr) r = __hadd2(r, bh[j]);
+                        xh[j] = __hadd2(r, xh[j]);
+                    }
+                    if (writer) *reinterpret_cast<uint4*>(pro.x_out + (size_t)b * k + vi * 8) = v;
+                }
+                *reinterpret_cast<uint4*>(xs + (size_t)b * pitch + vi * 8) = v;
+                const __half2* vh = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(vh[j]);
+                    s += f.x + f.y;
+                    ss += f.x * f.x + f.y * f.y;
+                }
+            }
+            s = warp_sum(s);
+            ss = warp_sum(ss);
+            if (lane == 0) {
+                pred[2 * cw_of(warp)] = s;
+                pred[2 * cw_of(warp) + 1] = ss;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            float ts = 0.f, tss = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                ts += pred[2 * w];
+                tss += pred[2 * w + 1];
+            }
+            const float mean = ts / k;
+            const float rstd = rsqrtf(tss / k - mean * mean + pro.eps);
+            const __half2 mean_h = __float2half2_rn(mean), rstd_h = __float2half2_rn(rstd);
+            for (int vi = ct; vi < nvec; vi += 256) {
+                uint4 v = *reinterpret_cast<uint4*>(xs + (size_t)b * pitch + vi * 8);
+                const uint4 gq = ld_ro_16(pro.gamma + vi * 8);
+                const uint4 bq = ld_ro_16(pro.beta + vi * 8);
+                const __half2* gh = reinterpret_cast<const __half2*>(&gq);
+                const __half2* bh = reinterpret_cast<const __half2*>(&bq);
+                __half2* vh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) vh[j] = __hadd2_rn(__hmul2_rn(__hmul2_rn(__hsub2_rn(vh[j], mean_h), rstd_h), gh[j]), bh[j]);
+                *reinterpret_cast<uint4*>(xs + (size_t)b * pitch + vi * 8) = v;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int tok = min(m0 + mt * 8 + g, m - 1);
+            xrow[mt] = xs + (size_t)tok * pitch + ks * KSTEP + t * 2 * EPC;
+        }
+    } else {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int tok = min(m0 + mt * 8 + g, m - 1);
+            xrow[mt] = x + (size_t)tok * k + ks * KSTEP + t * 2 * EPC;
+        }
     }
     int i = 0;
     for (int pass = 0; pass < passes; ++pass) {
@@ -161,9 +265,13 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __half* __re
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int q = 0; q < XV; ++q) xv[mt][q] = ld_ro_16(xrow[mt] + (size_t)kc * (CHUNK / (int)sizeof(WT)) + q * 8);
+                    for (int q = 0; q < XV; ++q) {
+                        if constexpr (PRO) xv[mt][q] = *reinterpret_cast<const uint4*>(xrow[mt] + (size_t)kc * (CHUNK / (int)sizeof(WT)) + q * 8);
+                        else xv[mt][q] = ld_ro_16(xrow[mt] + (size_t)kc * (CHUNK / (int)sizeof(WT)) + q * 8);
+                    }
             }
             mbar_wait(&bar_full[s], ph);
+            if (i == 0) trc_t2 = trc_now(trc_who);
             if (active) {
                 // box layout: row r at r * 128 bytes, 16-byte chunk c stored at chunk (c ^ (r & 7))  (SWIZZLE_128B)
                 const int rl = tile * 16 + g;                      // rl & 7 == (rl + 8) & 7 == g & 7
@@ -235,7 +343,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __half* __re
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    if (threadIdx.x == 32) trc_emit(sizeof(WT) == 1 ? TRC_GEMM_W8 : TRC_GEMM_F16, trc_t0, trc_t1, trc_t2, n, k);
 }
+
+FTCF_TRACE_INSTALLER(trace_install_gemm_skinny)
 
 static int skinny_rows_per_cta(int n)
 {
@@ -248,7 +359,7 @@ static int skinny_rows_per_cta(int n)
 
 template <typename WT, int EPI>
 static int launch_skinny(const void* x, const void* w, const void* scale, const void* bias, void* y, int m, int n, int k,
-                         int ldy, int act, const ftcf_prefetch_hint* next, cudaStream_t st)
+                         int ldy, int act, const ftcf_prefetch_hint* next, cudaStream_t st, const SkPro* pro = nullptr)
 {
     constexpr int EPC = 16 / sizeof(WT);
     FTCF_REQUIRE(k % (8 * EPC) == 0, FTCF_ERR_UNSUPPORTED, "skinny gemm: k=%d must be a multiple of %d", k, 8 * EPC);
@@ -258,6 +369,7 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
     const uint8_t* next_w = nullptr;
     int next_n = 0, next_row_bytes = 0, next_rpc = 1;
     const int next_pf = g_sk_prefetch_rows.load(std::memory_order_relaxed);
+    const int pf_ahead = g_sk_pf_ahead.load(std::memory_order_relaxed);
     if (next != nullptr && next->w != nullptr && next_pf > 0 && next->row_bytes % 16 == 0) {
         next_w = static_cast<const uint8_t*>(next->w);
         next_n = next->n;
@@ -266,7 +378,16 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
     }
     const dim3 grid(ceil_div(n, rows_per_cta), ceil_div(m, 8 * mt));
     const dim3 block(sk::THREADS);
-    const size_t smem = (size_t)sk::STAGES * sk::STAGE_BYTES + 1024;
+    size_t smem = (size_t)sk::STAGES * sk::STAGE_BYTES + 1024;
+    SkPro prov{};
+    if (pro != nullptr) {
+        FTCF_REQUIRE(m <= 4, FTCF_ERR_UNSUPPORTED, "skinny gemm: the fused LayerNorm prologue takes m <= 4 rows (m=%d)", m);
+        FTCF_REQUIRE(pro->x && pro->gamma && pro->beta && (pro->add_ffn == nullptr) == (pro->add_attn == nullptr), FTCF_ERR_INVALID,
+                     "skinny gemm: incomplete prologue");
+        prov = *pro;
+        smem += (size_t)m * (k + 8) * sizeof(__half);
+        FTCF_REQUIRE(smem <= 200 * 1024, FTCF_ERR_UNSUPPORTED, "skinny gemm: prologue rows do not fit shared memory (m=%d k=%d)", m, k);
+    }
     const __half* xs = static_cast<const __half*>(x);
     CUtensorMap mw;
     {
@@ -276,16 +397,25 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
     const __half* sc = static_cast<const __half*>(scale);
     const __half* bs = static_cast<const __half*>(bias);
     cudaError_t err = cudaSuccess;
-#define FTCF_SK(MT_)                                                                                                    \
+#define FTCF_SK_(MT_, PRO_)                                                                                             \
     do {                                                                                                                \
-        static bool configured = false;                                                                                 \
-        if (!configured) {                                                                                              \
-            err = cudaFuncSetAttribute(gemm_skinny_kernel<WT, MT_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            configured = true;                                                                                          \
+        static size_t configured = 0;                                                                                   \
+        if (configured < smem) {                                                                                        \
+            err = cudaFuncSetAttribute(gemm_skinny_kernel<WT, MT_, EPI, PRO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (err == cudaSuccess && g_sk_carveout.load())                                                             \
+                err = cudaFuncSetAttribute(gemm_skinny_kernel<WT, MT_, EPI, PRO_>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared); \
+            configured = smem;                                                                                          \
         }                                                                                                               \
         if (err == cudaSuccess)                                                                                         \
-            err = launch_pdl(gemm_skinny_kernel<WT, MT_, EPI>, grid, block, smem, st, mw, xs, sc, bs, y, m, n, k, ldy, act, rows_per_cta, next_w, next_n, next_row_bytes, next_rpc, next_pf); \
+            err = launch_pdl(gemm_skinny_kernel<WT, MT_, EPI, PRO_>, grid, block, smem, st, mw, prov, xs, sc, bs, y, m, n, k, ldy, act, rows_per_cta, next_w, next_n, next_row_bytes, next_rpc, next_pf, pf_ahead); \
     } while (0)
+#define FTCF_SK(MT_) FTCF_SK_(MT_, false)
+    if (pro != nullptr) {
+        FTCF_SK_(1, true);
+        FTCF_REQUIRE(err == cudaSuccess, FTCF_ERR_CUDA, "skinny gemm (fused prologue) launch failed: %s", cudaGetErrorString(err));
+        FTCF_LAUNCH_CHECK();
+        return FTCF_OK;
+    }
     switch (mt) {
         case 1: FTCF_SK(1); break;
         case 2: FTCF_SK(2); break;
@@ -293,6 +423,7 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
         default: FTCF_SK(4); break;
     }
 #undef FTCF_SK
+#undef FTCF_SK_
     FTCF_REQUIRE(err == cudaSuccess, FTCF_ERR_CUDA, "skinny gemm launch failed: %s", cudaGetErrorString(err));
     FTCF_LAUNCH_CHECK();
     return FTCF_OK;
@@ -309,6 +440,33 @@ int gemm_f16_skinny(const void* x, const void* w_nk, const void* bias, void* y, 
 {
     if (out_f32) return launch_skinny<__half, EPI_F32>(x, w_nk, nullptr, bias, y, m, n, k, ldy, act, next, st);
     return launch_skinny<__half, EPI_F16>(x, w_nk, nullptr, bias, y, m, n, k, ldy, act, next, st);
+}
+
+static SkPro to_skpro(const ftcf_ln_prologue& p)
+{
+    SkPro r{};
+    r.x = static_cast<const __half*>(p.x);
+    r.add_ffn = static_cast<const __half*>(p.add_ffn);
+    r.add_attn = static_cast<const __half*>(p.add_attn);
+    r.add_bias = static_cast<const __half*>(p.add_bias);
+    r.gamma = static_cast<const __half*>(p.gamma);
+    r.beta = static_cast<const __half*>(p.beta);
+    r.x_out = static_cast<__half*>(p.x_out);
+    r.eps = p.eps;
+    return r;
+}
+int gemm_w8a16_skinny_ln(const ftcf_ln_prologue& pro, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n, int k,
+                         int act, cudaStream_t st)
+{
+    const SkPro sp = to_skpro(pro);
+    return launch_skinny<uint8_t, EPI_W8>(pro.x, w_nk, scale, bias, y, m, n, k, n, act, nullptr, st, &sp);
+}
+int gemm_f16_skinny_ln(const ftcf_ln_prologue& pro, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
+                       int out_f32, cudaStream_t st)
+{
+    const SkPro sp = to_skpro(pro);
+    if (out_f32) return launch_skinny<__half, EPI_F32>(pro.x, w_nk, nullptr, bias, y, m, n, k, ldy, act, nullptr, st, &sp);
+    return launch_skinny<__half, EPI_F16>(pro.x, w_nk, nullptr, bias, y, m, n, k, ldy, act, nullptr, st, &sp);
 }
 
 // ---------------------------------------------------------------- fp16 [k,n] -> [n,k]

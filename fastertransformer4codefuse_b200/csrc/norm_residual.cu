@@ -21,6 +21,7 @@ layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ add1, 
                  __half* __restrict__ y, int n, float eps)
 {
     __shared__ float red[32];
+    const unsigned long long trc_t0 = trc_now(threadIdx.x == 0);
     const size_t row = blockIdx.x;
     const int nvec = n >> 3;   // 8 halves per vector
     uint4 v[LN_MAX_VEC];
@@ -80,6 +81,7 @@ layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ add1, 
             *reinterpret_cast<uint4*>(y + row * n + vi * 8) = v[i];
         }
     }
+    if (threadIdx.x == 0) trc_emit(TRC_LN, trc_t0, trc_t0, trc_t0, n, PRE);
 }
 
 // MODE 0: out = ((ffn + attn) + bias) + (tp > 1 ? half(x / tp) : x)      (parallel residual)
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(256)
 residual_kernel(__half* __restrict__ out, const __half* __restrict__ a, const __half* __restrict__ b,
                 const __half* __restrict__ x, const __half* __restrict__ bias, int n, size_t total_vec, float inv_tp)
 {
+    const unsigned long long trc_t0 = trc_now(threadIdx.x == 0);
     const size_t vi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vi >= total_vec) return;
     const int col = (int)((vi * 8) % n);
@@ -122,6 +125,7 @@ residual_kernel(__half* __restrict__ out, const __half* __restrict__ a, const __
         }
     }
     *reinterpret_cast<uint4*>(out + vi * 8) = av;
+    if (threadIdx.x == 0) trc_emit(TRC_RESIDUAL, trc_t0, trc_t0, trc_t0, n, MODE);
 }
 
 __global__ void __launch_bounds__(256)
@@ -136,6 +140,8 @@ embedding_kernel(__half* __restrict__ out, const __half* __restrict__ table, con
     id = min(max(id, 0), vocab - 1);
     *reinterpret_cast<uint4*>(out + (size_t)row * n + c * 8) = ld_ro_16(table + (size_t)id * n + c * 8);
 }
+
+FTCF_TRACE_INSTALLER(trace_install_norm_residual)
 
 static int ln_threads(int n)
 {

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(1024) logits_prepare_kernel(const ftcf_samplin
 {
     __shared__ float s_red[32];
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) { const unsigned long long t = trc_now(); trc_emit(TRC_SAMPLING, t, t, t, 0, 0); }   // marks the start of sampling
     const int V = p.vocab, Vp = p.vocab_padded;
     float* row = p.logits + (size_t)b * Vp;
     const int step = *p.step;
@@ -253,6 +254,7 @@ topk_stage2_kernel(const ftcf_sampling_params p, int* __restrict__ cand_id, floa
 __global__ void __launch_bounds__(256) step_finalize_kernel(const ftcf_sampling_params p)
 {
     __shared__ int s_cnt;
+    const unsigned long long trc_t0 = trc_now(threadIdx.x == 0);
     const int step = *p.step;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
@@ -286,8 +288,11 @@ __global__ void __launch_bounds__(256) step_finalize_kernel(const ftcf_sampling_
             p.finished_count_host_mapped[1] = step;
         }
         *p.step = step + 1;
+        trc_emit(TRC_SAMPLING, trc_t0, trc_t0, trc_t0, step, 3);   // marks the end of the step
     }
 }
+
+FTCF_TRACE_INSTALLER(trace_install_sampling)
 
 __global__ void curand_init_kernel(curandState_t* st, const uint64_t* seeds, int batch)
 {

@@ -53,6 +53,11 @@ __device__ __forceinline__ void load_2d(void* smem_dst, const CUtensorMap* map, 
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// L2 prefetch of one box of the tensor map (no shared-memory destination, no barrier)
+__device__ __forceinline__ void prefetch_2d(const CUtensorMap* map, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 }  // namespace tma
 #endif
 

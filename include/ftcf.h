@@ -46,6 +46,13 @@ long long ftcf_launch_count(void);
  * "skinny_target_ctas" CTAs per skinny-GEMM launch, "skinny_prefetch_rows" rows each CTA prefetches into L2 up front. */
 int ftcf_set_tunable(const char* name, int value);
 
+/* Debug: per-CTA timeline of the decode kernels.  Between start and stop every instrumented kernel appends one 56-byte record
+ * per CTA {u64 t_start, t_after_dependency_wait, t_first_data, t_end (globaltimer ns); i32 kind, cta, n_cta, a, b, pad}
+ * (kind: 1 int8 GEMM, 2 fp16 GEMM [a = n, b = k], 10 decode attention, 20 LayerNorm, 21 residual, 30 sampling).
+ * tools/trace_step.py turns it into a per-launch timeline of one decode step. */
+int ftcf_debug_trace_start(unsigned capacity);
+int ftcf_debug_trace_stop(void* out_host, unsigned max_records, unsigned* n);
+
 /* ------------------------------------------------------------------------------------------------
  * Weight-only INT8 quantiser (CPU).  Replaces ft::symmetric_quantize<half,half|float> +
  * preprocess_weights_for_mixed_gemm, kernels/cutlass_kernels/cutlass_preprocessors.cc:577-673,500-539,
@@ -93,6 +100,22 @@ int ftcf_gemm_f16(const void* x, const void* w_nk, const void* bias, void* y, in
                   int out_f32, int impl, void* stream);
 int ftcf_gemm_f16_ex(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
                      int out_f32, int impl, const ftcf_prefetch_hint* next, void* stream);
+
+/* Decode-step variants (m <= 4 rows) with the layer's glue fused in as a prologue: every CTA first builds its input
+ *   r = ((add_ffn + add_attn) + add_bias) + x     -- the previous layer's parallel-residual add (skipped when add_ffn is NULL)
+ *   a = LayerNorm(r; gamma, beta, eps)            -- fp32 statistics, fp16 normalisation
+ * in shared memory and the GEMM runs on `a`; x_out (optional) receives r.  Same arithmetic as
+ * ftcf_add_bias_attn_ffn_residual (tp = 1) followed by ftcf_layernorm (kernels/add_residual_kernels.cu:116-176,
+ * kernels/layernorm_kernels.cu:158-286), without their two launches on the layer's critical path. */
+typedef struct {
+    const void *x, *add_ffn, *add_attn, *add_bias, *gamma, *beta;   /* fp16: [m,k] [m,k] [m,k] [k] [k] [k] */
+    void* x_out;                                                    /* [m,k] fp16 or NULL; must not alias x */
+    float eps;
+} ftcf_ln_prologue;
+int ftcf_gemm_w8a16_ln(const ftcf_ln_prologue* pro, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m,
+                       int n, int k, int act, void* stream);
+int ftcf_gemm_f16_ln(const ftcf_ln_prologue* pro, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy,
+                     int act, int out_f32, void* stream);
 
 /* out[k,n] -> out_t[n,k] fp16 transpose (load-time re-layout of fp16 weights to K-major). */
 int ftcf_transpose_f16(const void* in_kn, void* out_nk, int k, int n, void* stream);

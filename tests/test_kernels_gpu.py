@@ -371,3 +371,74 @@ def test_f16_tcgen05(lib, cuda, m, out_f32):
         assert_close("tcgen05 f16 gemm fp32 out", y.cpu(), ref.cpu(), rtol=1e-4, atol=1e-4)
     else:
         assert_close("tcgen05 f16 gemm fp16 out", y.float().cpu(), ref.cpu(), rtol=1e-3, atol=1e-3)
+
+
+def _ln_prologue(x, ffn, attn, bias, g, b, x_out):
+    pro = capi.LnPrologue()
+    pro.x, pro.gamma, pro.beta, pro.eps = x.data_ptr(), g.data_ptr(), b.data_ptr(), 1e-5
+    if ffn is not None:
+        pro.add_ffn, pro.add_attn = ffn.data_ptr(), attn.data_ptr()
+        pro.add_bias = bias.data_ptr() if bias is not None else None
+    pro.x_out = x_out.data_ptr() if x_out is not None else None
+    return pro
+
+
+@pytest.mark.parametrize("m", [1, 2, 4])
+@pytest.mark.parametrize("with_res", [False, True])
+@pytest.mark.parametrize("n,k", [(1024, 5120), (300, 256)])
+def test_w8a16_fused_residual_layernorm_prologue(lib, cuda, m, with_res, n, k):
+    """ftcf_gemm_w8a16_ln == residual add (exact fp16 adds) -> LayerNorm -> INT8 GEMM; the stored residual stream is exact."""
+    torch.manual_seed(100 * m + n + int(with_res))
+    w = (torch.randn(k, n, device=cuda) * 0.02).half()
+    p, s, q = _quant(w)
+    x, ffn, attn = [torch.randn(m, k, device=cuda).half() for _ in range(3)]
+    bias = (0.1 * torch.randn(k, device=cuda)).half()
+    g = (1 + 0.1 * torch.randn(k, device=cuda)).half()
+    b = (0.1 * torch.randn(k, device=cuda)).half()
+    obias = (0.1 * torch.randn(n, device=cuda)).half()
+    x_out = torch.zeros_like(x)
+    y = torch.empty(m, n, dtype=torch.float16, device=cuda)
+    pro = _ln_prologue(x, ffn if with_res else None, attn, bias, g, b, x_out if with_res else None)
+    capi.check(lib.ftcf_gemm_w8a16_ln(pro, p.data_ptr(), s.data_ptr(), obias.data_ptr(), y.data_ptr(), m, n, k, 1, stream()))
+    torch.cuda.synchronize()
+    r = x.float().cpu()
+    if with_res:
+        r = R.h(R.h(R.h(ffn.float().cpu() + attn.float().cpu()) + bias.float().cpu()) + r)
+        assert torch.equal(x_out.float().cpu(), r)
+    a = R.layernorm_ref(r, g.cpu(), b.cpu(), 1e-5)
+    # the same input through the unfused kernels must give the same GEMM result up to LayerNorm's reduction-order ulp
+    a_dev = a.half().to(cuda)
+    y2 = torch.empty_like(y)
+    capi.check(lib.ftcf_gemm_w8a16(a_dev.data_ptr(), p.data_ptr(), s.data_ptr(), obias.data_ptr(), y2.data_ptr(), m, n, k, 1, 1, stream()))
+    torch.cuda.synchronize()
+    ref = R.gelu_f32(a.float() @ (q.float().cpu() * s.float().cpu()[None, :]) + obias.float().cpu())
+    assert_close("fused-prologue gemm vs unfused", y.float().cpu(), y2.float().cpu(), rtol=4e-3, atol=4e-3)
+    assert_close("fused-prologue gemm vs oracle", y.float().cpu(), ref, rtol=4e-3, atol=6e-3)
+
+
+@pytest.mark.parametrize("out_f32", [0, 1])
+def test_f16_fused_layernorm_prologue(lib, cuda, out_f32):
+    torch.manual_seed(5 + out_f32)
+    m, n, k = 2, 520, 768
+    w = (torch.randn(n, k, device=cuda) * 0.02).half()        # K-major [n, k]
+    x, ffn, attn = [torch.randn(m, k, device=cuda).half() for _ in range(3)]
+    g = (1 + 0.1 * torch.randn(k, device=cuda)).half()
+    b = (0.1 * torch.randn(k, device=cuda)).half()
+    y = torch.empty(m, n, dtype=torch.float32 if out_f32 else torch.float16, device=cuda)
+    pro = _ln_prologue(x, ffn, attn, None, g, b, None)
+    capi.check(lib.ftcf_gemm_f16_ln(pro, w.data_ptr(), None, y.data_ptr(), m, n, k, n, 0, out_f32, stream()))
+    torch.cuda.synchronize()
+    r = R.h(R.h(ffn.float().cpu() + attn.float().cpu()) + x.float().cpu())
+    a = R.layernorm_ref(r, g.cpu(), b.cpu(), 1e-5)
+    ref = a.float() @ w.float().cpu().T
+    assert_close("fused-prologue f16 gemm", y.float().cpu(), ref, rtol=4e-3, atol=6e-3)
+
+
+def test_fused_prologue_rejects_large_m(lib, cuda):
+    x = torch.zeros(5, 256, dtype=torch.float16, device=cuda)
+    g = torch.ones(256, dtype=torch.float16, device=cuda)
+    w = torch.zeros(64, 256, dtype=torch.uint8, device=cuda)
+    sc = torch.ones(64, dtype=torch.float16, device=cuda)
+    y = torch.empty(5, 64, dtype=torch.float16, device=cuda)
+    pro = _ln_prologue(x, None, None, None, g, g, None)
+    assert lib.ftcf_gemm_w8a16_ln(pro, w.data_ptr(), sc.data_ptr(), None, y.data_ptr(), 5, 64, 256, 0, stream()) == 4   # FTCF_ERR_UNSUPPORTED

@@ -18,7 +18,8 @@ LOGIT_RTOL, LOGIT_ATOL = 2e-2, 3e-2
 
 
 def _build(cfg, int8_mode, cuda, seed=0, mega=1, tweak=None):
-    """mega = 1: the persistent decode-step kernel (decode_mega.cu) where it applies; 0: one kernel per operator."""
+    """mega = 1: the persistent decode-step kernel (decode_mega.cu) where it applies; 0: one kernel per operator with the
+    residual + LayerNorm prologue fused into the GEMMs (batch <= 4); -1: one kernel per operator, nothing fused."""
     rw = W.make_synthetic(cfg, 1, 0, int8_mode, "cpu", seed=seed, keep_plain=True)
     if tweak is not None:
         tweak(rw)
@@ -26,7 +27,8 @@ def _build(cfg, int8_mode, cuda, seed=0, mega=1, tweak=None):
     w, q, s = to_cuda_lists(rw, cuda)
     op = GptNeoXOp(None, 0, cfg.head_num, cfg.size_per_head, cfg.inter_size, cfg.layer_num, cfg.vocab_size,
                    cfg.rotary_embedding_dim, cfg.start_id, cfg.end_id, 1, 1, int8_mode, 1024, cfg.use_gptj_residual, w, q, s)
-    op.set_option("mega", mega)
+    op.set_option("mega", 1 if mega == 1 else 0)
+    op.set_option("fused_ln", 0 if mega == -1 else 1)
     return op, ref
 
 
@@ -63,7 +65,7 @@ def _compare(op, ref, cuda, ids, lens, out_len, graph, **kw):
     return res, exp
 
 
-@pytest.mark.parametrize("mega", [0, 1])
+@pytest.mark.parametrize("mega", [-1, 0, 1])
 @pytest.mark.parametrize("int8_mode", [0, 1])
 @pytest.mark.parametrize("graph", [False, True])
 def test_greedy_full_batch(cuda, int8_mode, graph, mega):
@@ -73,7 +75,7 @@ def test_greedy_full_batch(cuda, int8_mode, graph, mega):
     _compare(op, ref, cuda, ids, [12, 12], 10, graph)
 
 
-@pytest.mark.parametrize("mega", [0, 1])
+@pytest.mark.parametrize("mega", [-1, 0, 1])
 @pytest.mark.parametrize("int8_mode", [0, 1])
 def test_greedy_ragged_batch(cuda, int8_mode, mega):
     cfg = tiny_cfg()
@@ -92,7 +94,7 @@ def test_sequential_residual(cuda):
     _compare(op, ref, cuda, ids, lens, 6, False)
 
 
-@pytest.mark.parametrize("mega", [0, 1])
+@pytest.mark.parametrize("mega", [-1, 0, 1])
 def test_dh128_full_rotary(cuda, mega):
     cfg = tiny_cfg(head_num=2, size_per_head=128, rotary_embedding_dim=128, inter_size=1024, layer_num=3)
     op, ref = _build(cfg, 1, cuda, seed=11, mega=mega)
@@ -102,7 +104,7 @@ def test_dh128_full_rotary(cuda, mega):
     _compare(op, ref, cuda, ids, lens, 12, True)
 
 
-@pytest.mark.parametrize("mega", [0, 1])
+@pytest.mark.parametrize("mega", [-1, 0, 1])
 def test_seeded_topk_sampling_and_cum_log_probs(cuda, mega):
     cfg = tiny_cfg()
     op, ref = _build(cfg, 1, cuda, seed=1, mega=mega)
@@ -112,7 +114,7 @@ def test_seeded_topk_sampling_and_cum_log_probs(cuda, mega):
              repetition_penalty=[1.1, 1.1, 1.1], random_seed=[42, 42, 43], return_cum_log_probs=1)
 
 
-@pytest.mark.parametrize("mega", [0, 1])
+@pytest.mark.parametrize("mega", [-1, 0, 1])
 def test_single_token_prompt_runs_decoder_only(cuda, mega):
     cfg = tiny_cfg()
     op, ref = _build(cfg, 1, cuda, seed=2, mega=mega)
@@ -137,7 +139,7 @@ def test_mega_long_context_batch8(cuda, int8_mode):
     assert torch.equal(res_g[0], res_k[0])
 
 
-@pytest.mark.parametrize("mega", [0, 1])
+@pytest.mark.parametrize("mega", [-1, 0, 1])
 def test_finished_rows_stop_advancing(cuda, mega):
     """Rows that sample end_id stop (their attention work disappears from the schedule, the sampler pins them to end_id)
     while the others go on; the request ends early once every row is finished.  The end_id row of the LM head is scaled up

@@ -67,36 +67,25 @@ int main(int argc, char** argv)
         printf("%-58s %8.3f ms  %8.1f GB/s\n", name, ms, bytes / (ms * 1e-3) / 1e9);
     };
 
-    for (int pf : {0, 16, 32, 64, 128}) {
-        for (int ctas : {296, 444}) {
-            const int pdl = 0;
-            ftcf_set_tunable("skinny_prefetch_rows", pf);
-            ftcf_set_tunable("pdl", pdl);
+    // per-shape: 40 launches of ONE shape (different weights each), graph + PDL -> GB/s of that shape in a dependent chain
+    for (int ctas : {296, 444, 592})
+        for (int i = 0; i < 4; ++i) {
+            ftcf_set_tunable("skinny_prefetch_rows", 0);
+            ftcf_set_tunable("skinny_pf_ahead", 0);
+            ftcf_set_tunable("pdl", 1);
             ftcf_set_tunable("skinny_target_ctas", ctas);
-            char name[128];
-            // (a) one launch per matrix shape but covering ALL layers' rows: n = L * n_i (same k)  -> 4 big launches
-            snprintf(name, sizeof(name), "m=%d pf=%d ctas=%d: 3 big launches (k=5120, all layers)", m, pf, ctas);
-            timed(name, [&]() {
-                // treat the whole buffer as [rows, 5120]: total bytes / 5120 rows (valid because every matrix is K-major bytes)
-                const size_t rows = (size_t)(3 * h + h + inter) * L;   // k = 5120 part: 40960 rows per layer
-                const size_t per = rows / 3;
-                for (int j = 0; j < 3; ++j) FK(ftcf_gemm_w8a16(x, w + j * per * 5120, scale, nullptr, y, m, (int)per > 20480 * 16 ? 20480 * 16 : (int)per, 5120, 0, 1, st));
-            }, 3.0 * 20480 * 16 * 5120, 3);
-            // (b) the real chain, plain stream launches
-            snprintf(name, sizeof(name), "m=%d pf=%d ctas=%d: 160-launch chain, stream", m, pf, ctas);
-            timed(name, chain, (double)total * L, 5);
-            // (c) the real chain, captured into a graph
+            const size_t bytes = (size_t)ks[i] * ns[i];
             cudaGraph_t g;
             cudaGraphExec_t ge;
             CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            chain();
+            for (int l = 0; l < L; ++l) FK(ftcf_gemm_w8a16(x, w + (size_t)l * total, scale, nullptr, y, m, ns[i], ks[i], 0, 1, st));
             CK(cudaStreamEndCapture(st, &g));
             CK(cudaGraphInstantiate(&ge, g, 0));
-            snprintf(name, sizeof(name), "m=%d pf=%d ctas=%d: 160-launch chain, graph", m, pf, ctas);
-            timed(name, [&]() { CK(cudaGraphLaunch(ge, st)); }, (double)total * L, 10);
+            char name[128];
+            snprintf(name, sizeof(name), "m=%d ctas=%d: 40 x (n=%d, k=%d) chain, graph+pdl", m, ctas, ns[i], ks[i]);
+            timed(name, [&]() { CK(cudaGraphLaunch(ge, st)); }, (double)bytes * L, 10);
             cudaGraphExecDestroy(ge);
             cudaGraphDestroy(g);
         }
-    }
     return 0;
 }
