@@ -682,14 +682,14 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     std::vector<float> ps(B), temps(B, 1.f), reps(B, 1.f);
     std::vector<uint64_t> seeds(B, 0);
     int max_top_k = 1;
-    bool any_temp = false, any_rep = false;
+    bool any_temp = false, any_rep = false, any_topp = false;
     for (int b = 0; b < B; ++b) {
         int k = r.top_k_host ? *pick(r.top_k_host, r.n_top_k, b) : 0;
         float p = r.top_p_host ? *pick(r.top_p_host, r.n_top_p, b) : 0.f;
         if (k < 0) k = 0;
         if (k == 0 && p == 0.f) k = 1;
         if (k > 0 && p == 0.f) p = 1.f;
-        FTCF_REQUIRE(k > 0, FTCF_ERR_UNSUPPORTED, "forward: top_k = 0 with top_p > 0 (pure top-p sampling) is not implemented yet");
+        any_topp |= k == 0;                     // pure top-p row (TopPSamplingLayer.cu:60-78)
         if (k > 1024) k = 1024;
         p = std::min(std::max(p, 0.f), 1.f);
         ks[b] = k;
@@ -838,6 +838,7 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     sp.workspace = e->samp_ws.p;
     sp.batch = B; sp.vocab = c.vocab_size; sp.vocab_padded = e->Vp; sp.max_top_k = max_top_k;
     sp.max_input_len = S; sp.max_len = max_len; sp.end_id = c.end_id; sp.want_probs = r.return_cum_log_probs ? 1 : 0;
+    sp.has_top_p_rows = any_topp ? 1 : 0;
 
     cudaEvent_t ev0, ev1, ev2;
     FTCF_CUDA_CHECK(cudaEventCreate(&ev0));
@@ -887,7 +888,7 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     const bool use_graph = e->opt_cuda_graph != 0 && out_len > 2 && !want_trace;
     char keybuf[256];
     snprintf(keybuf, sizeof(keybuf), "B%d S%d M%d k%d t%d r%d p%d l%p s%p n%d/%d kv%p x%p sm%p lg%p f%d", B, S, max_len, max_top_k, (int)any_temp,
-             (int)any_rep, sp.want_probs, (const void*)sp.optional_last_tokens, (const void*)sp.stop_words, sp.n_last, sp.n_stop, e->kv.p, e->x.p,
+             (int)any_rep + 2 * (int)any_topp, sp.want_probs, (const void*)sp.optional_last_tokens, (const void*)sp.stop_words, sp.n_last, sp.n_stop, e->kv.p, e->x.p,
              e->small.p, e->logits.p, (int)e->fused_on);
     const std::string key(keybuf);
 

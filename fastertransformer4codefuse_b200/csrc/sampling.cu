@@ -125,8 +125,9 @@ __global__ void __launch_bounds__(1024) logits_prepare_kernel(const ftcf_samplin
         else if (fin) row[v] = (v == p.end_id) ? FLT_MAX : -FLT_MAX;
     }
     __syncthreads();
-    // (e) softmax
-    if (p.want_probs) {
+    // (e) softmax: when cum_log_probs are wanted (TopKSamplingLayer.cu:236-247) and always for pure top-p rows
+    //     (TopPSamplingLayer.cu:293-300)
+    if (p.want_probs || p.top_k[b] == 0) {
         float mx = -FLT_MAX;
         for (int v = tid; v < Vp; v += nt) mx = fmaxf(mx, row[v]);
         mx = block_max(mx, s_red);
@@ -153,6 +154,7 @@ topk_stage1_kernel(const float* __restrict__ logits, float* __restrict__ tmp, in
     const int lane_blk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     if (finished[b]) return;
     const int k = top_k[b];
+    if (k == 0) return;                       // pure top-p row: topp_sample_kernel (skip_decode, TopKSamplingLayer.cu:66-75)
     const float* row = logits + (size_t)b * Vp;
     float* trow = tmp + (size_t)b * Vp;
     for (int e = tid + lane_blk * BS; e < Vp; e += BS * BLOCKS_PER_ROW) trow[e] = row[e];
@@ -188,6 +190,7 @@ topk_stage2_kernel(const ftcf_sampling_params p, int* __restrict__ cand_id, floa
     const int b = blockIdx.x, tid = threadIdx.x;
     const int step = *p.step;
     int32_t* out = p.output_ids + (size_t)step * p.batch + b;
+    if (p.top_k[b] == 0) return;              // pure top-p row
     if (p.finished[b]) {
         if (tid == 0) *out = p.end_id;
         return;
@@ -247,6 +250,136 @@ topk_stage2_kernel(const ftcf_sampling_params p, int* __restrict__ cand_id, floa
         if (p.cum_log_probs != nullptr && p.want_probs) p.cum_log_probs[b] += logf(s_val2[chosen]);
         p.seq_len[b] += 1;
         p.finished[b] = (tok == p.end_id) ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------- pure top-p (nucleus) rows: one CTA per row
+// Semantics of topp_beam_topk_kernel<MAX_K = 1> + the segmented descending radix sort + topp_sampling
+// (kernels/sampling_topp_kernels.cu:801-1004, 1006-1160): draw r = curand_uniform * p; if the largest probability alone reaches
+// p it is taken; otherwise walk the probabilities in descending order (ties in ascending id order: the sort is stable) and take
+// the first id whose inclusive cumulative sum reaches r.
+// B200 design: no sort.  The crossing element is found by bisection on the probability's bit pattern (non-negative floats order
+// like unsigned integers): G(K) = sum of the probabilities with key >= K is evaluated by one pass over the row (400 KB, L2
+// resident) per bisection step, in 2^-44 fixed point so that the sum does not depend on the order of the additions -- 31 passes,
+// deterministic, O(V) memory traffic from L2 and no V-sized scratch.
+__device__ __forceinline__ unsigned long long prob_fx(float pr) { return __float2ull_rz(pr * 17592186044416.f); }   // 2^44
+
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    unsigned long long r = lane < nw ? red[lane] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    return r;
+}
+
+__global__ void __launch_bounds__(1024) topp_sample_kernel(const ftcf_sampling_params p)
+{
+    __shared__ unsigned long long s_red[32];
+    __shared__ Cand s_c[32];
+    __shared__ float s_rand;
+    __shared__ int s_pick;
+    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    if (p.top_k[b] != 0) return;
+    const int step = *p.step;
+    int32_t* out = p.output_ids + (size_t)step * p.batch + b;
+    if (p.finished[b]) {
+        if (tid == 0) *out = p.end_id;
+        return;
+    }
+    const int Vp = p.vocab_padded;
+    const float* row = p.logits + (size_t)b * Vp;      // probabilities (logits_prepare softmaxed this row)
+    const float pthr = p.top_p[b];
+    if (tid == 0) {
+        curandState_t* st = reinterpret_cast<curandState_t*>(p.curand_states) + b;
+        s_rand = curand_uniform(st) * pthr;
+    }
+    // largest probability, lowest id on ties
+    Cand c{-FLT_MAX, -1};
+    for (int v = tid; v < Vp; v += nt) {
+        const float x = row[v];
+        if (x > c.v) {
+            c.v = x;
+            c.idx = v;
+        }
+    }
+    // block_argmax prefers the higher thread on ties (the top-k rule); for the top-p head any of the tied maxima has the same
+    // probability, so only the id differs in that measure-zero case
+    const Cand top = block_argmax<1024>(c, s_c);
+    __syncthreads();
+    int pick = top.idx;
+    float pick_prob = top.v;
+    if (!(top.v >= pthr)) {
+        const unsigned long long need = prob_fx(s_rand);
+        // invariant: G(lo) >= need > G(hi)
+        unsigned lo = 0u, hi = __float_as_uint(top.v) + 1u;
+        unsigned long long g_hi = 0ull;                       // G(hi)
+        {
+            unsigned long long t = 0ull;
+            for (int v = tid; v < Vp; v += nt) t += prob_fx(fmaxf(row[v], 0.f));
+            const unsigned long long total = block_sum_u64(t, s_red);
+            if (total < need) lo = hi;                        // rounding: r beyond the total mass -> keep the head
+        }
+        while (hi - lo > 1u) {
+            const unsigned mid = lo + ((hi - lo) >> 1);
+            unsigned long long t = 0ull;
+            for (int v = tid; v < Vp; v += nt) {
+                const float x = fmaxf(row[v], 0.f);
+                if (__float_as_uint(x) >= mid) t += prob_fx(x);
+            }
+            const unsigned long long g = block_sum_u64(t, s_red);
+            if (g >= need) lo = mid;
+            else {
+                hi = mid;
+                g_hi = g;
+            }
+        }
+        if (lo < hi) {
+            // elements with key == lo all carry the same probability; the crossing one is the j-th of them in id order
+            const float pk = __uint_as_float(lo);
+            const unsigned long long pk_fx = prob_fx(pk);
+            unsigned long long j = pk_fx > 0ull ? (need - g_hi + pk_fx - 1ull) / pk_fx : 1ull;
+            if (j < 1ull) j = 1ull;
+            if (tid == 0) s_pick = -1;
+            __syncthreads();
+            // ordered count over the row in chunks of the block size
+            unsigned long long seen = 0ull;
+            for (int base = 0; base < Vp && s_pick < 0; base += nt) {
+                const int v = base + tid;
+                const int hit = (v < Vp && __float_as_uint(fmaxf(row[v], 0.f)) == lo) ? 1 : 0;
+                // inclusive rank of this hit inside the chunk
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                const int lane = tid & 31, warp = tid >> 5;
+                const int in_warp = __popc(bal & ((2u << lane) - 1u));
+                __syncthreads();
+                if (lane == 0) s_red[warp] = (unsigned long long)__popc(bal);
+                __syncthreads();
+                unsigned long long before = 0ull, chunk_total = 0ull;
+                for (int w = 0; w < (nt >> 5); ++w) {
+                    const unsigned long long cw = s_red[w];
+                    if (w < warp) before += cw;
+                    chunk_total += cw;
+                }
+                if (hit && seen + before + (unsigned long long)in_warp == j) s_pick = v;
+                seen += chunk_total;
+                __syncthreads();
+            }
+            if (s_pick >= 0) {
+                pick = s_pick;
+                pick_prob = pk;
+            }
+        }
+    }
+    if (tid == 0) {
+        *out = pick;
+        if (p.cum_log_probs != nullptr && p.want_probs) p.cum_log_probs[b] += logf(pick_prob);
+        p.seq_len[b] += 1;
+        p.finished[b] = (pick == p.end_id) ? 1 : 0;
     }
 }
 
@@ -391,6 +524,10 @@ extern "C" int ftcf_sampling_step(const ftcf_sampling_params* pp, void* stream)
         topk_stage2_kernel<256><<<p.batch, 256, dyn, st>>>(p, cand_id, cand_val);
     }
     FTCF_LAUNCH_CHECK();
+    if (p.has_top_p_rows) {
+        topp_sample_kernel<<<p.batch, 1024, 0, st>>>(p);
+        FTCF_LAUNCH_CHECK();
+    }
     step_finalize_kernel<<<1, 256, 0, st>>>(p);
     FTCF_LAUNCH_CHECK();
     return FTCF_OK;

@@ -183,7 +183,7 @@ typedef struct {
     uint8_t* finished;             /* [B]                                                                    */
     float* cum_log_probs;          /* [B] or NULL                                                            */
     const int32_t* input_len;      /* [B]                                                                    */
-    const int32_t* top_k;          /* [B] runtime k (already through the setup rules)                        */
+    const int32_t* top_k;          /* [B] runtime k (already through the setup rules); 0 = pure top-p row    */
     const float* top_p;            /* [B]                                                                    */
     const float* temperature;      /* [B] or NULL (NULL == all 1)                                            */
     const float* repetition_penalty; /* [B] or NULL                                                          */
@@ -195,6 +195,7 @@ typedef struct {
     void* workspace;               /* ftcf_sampling_workspace_bytes()                                        */
     int32_t batch, vocab, vocab_padded, max_top_k, n_last, n_stop, max_input_len, max_len, end_id;
     int32_t want_probs;            /* 1: softmax before top-k and accumulate cum_log_probs                   */
+    int32_t has_top_p_rows;        /* 1: some row has top_k == 0 (pure top-p, layers/sampling_layers/TopPSamplingLayer.cu) */
 } ftcf_sampling_params;
 size_t ftcf_sampling_workspace_bytes(int batch, int vocab_padded, int max_top_k);
 size_t ftcf_curand_state_bytes(void);

@@ -203,6 +203,24 @@ def topk_sampling_row(row, k, p, rng: CurandXorwow, max_top_k, is_prob):
     raise AssertionError
 
 
+def topp_sampling_row(probs, p, rng: CurandXorwow):
+    """One unfinished pure top-p row (top_k == 0): topp_beam_topk_kernel<MAX_K=1> + stable descending sort + topp_sampling
+    (kernels/sampling_topp_kernels.cu:801-1004).  probs: fp32 softmax of the row.  Returns (token id, its probability).
+    The reference accumulates the sorted probabilities with cub::BlockScan in fp32; this restatement uses the exact
+    (float64) prefix sums, so the two can only differ when the draw falls within fp32 rounding of a prefix sum."""
+    rand = np.float32(rng.uniform() * np.float32(p))          # drawn before the head check (:917-920)
+    top = int(np.argmax(probs))
+    if np.float32(probs[top]) >= np.float32(p):               # :842-856
+        return top, np.float32(probs[top])
+    order = np.argsort(-probs.astype(np.float64), kind="stable")
+    cum = np.cumsum(probs[order].astype(np.float64))
+    hit = np.nonzero(cum >= np.float64(rand))[0]
+    if len(hit) == 0:
+        return top, np.float32(probs[top])
+    j = int(order[hit[0]])
+    return j, np.float32(probs[j])
+
+
 def stop_words_criterion(output_ids, stop_words, finished, step):
     """stop_criteria_kernels.cu:24-81.  output_ids [maxlen, B] time-major; stop_words [B, 2, n]."""
     B = output_ids.shape[1]

@@ -218,3 +218,13 @@ def test_pybind_shim_runs_the_reference_call(cuda):
     with pytest.raises(RuntimeError):
         op.forward(torch.from_numpy(ids), torch.tensor(lens, dtype=torch.int32, device=cuda), 8, 1, None, None, None, None, None,
                    None, None, None, None, 0, None)     # CPU input_ids
+
+
+def test_pure_top_p_request(cuda):
+    """top_k = 0 with top_p > 0 through the whole engine (graph replay), mixed with a top-k row."""
+    cfg = tiny_cfg()
+    op, ref = _build(cfg, 1, cuda, seed=8, mega=0)
+    lens = [10, 6]
+    ids = _prompts(2, 10, cfg.vocab_size, lens, seed=3)
+    _compare(op, ref, cuda, ids, lens, 12, True, top_k=[0, 3], top_p=[0.9, 0.8], temperature=[0.9, 1.0], random_seed=[21, 22],
+             return_cum_log_probs=1)

@@ -21,7 +21,7 @@ def _run_steps(lib, cuda, B, V, Vp, max_in, out_len, lens, top_k, top_p, tempera
     out_ids = np.zeros((max_len, B), dtype=np.int64)
     out_ids[:max_in] = prompt.T
     ks, ps, _ = S.setup_topk_runtime_args(top_k, top_p, B)
-    max_top_k = int(ks.max())
+    max_top_k = max(1, int(ks.max()))
     temp = np.broadcast_to(np.asarray(temperature, np.float32).reshape(-1), (B,)).copy()
     reps = np.broadcast_to(np.asarray(rep, np.float32).reshape(-1), (B,)).copy()
     seeds = np.broadcast_to(np.asarray(seeds, np.int64).reshape(-1), (B,)).copy()
@@ -54,7 +54,8 @@ def _run_steps(lib, cuda, B, V, Vp, max_in, out_len, lens, top_k, top_p, tempera
                              d_stop.data_ptr() if d_stop is not None else None,
                              states.data_ptr(), d_step.data_ptr(), flag.data_ptr(), ws.data_ptr(),
                              B, V, Vp, max_top_k, d_last.shape[1] if d_last is not None else 0,
-                             d_stop.shape[2] if d_stop is not None else 0, max_in, max_len, end_id, 1 if want_probs else 0)
+                             d_stop.shape[2] if d_stop is not None else 0, max_in, max_len, end_id, 1 if want_probs else 0,
+                             1 if (ks == 0).any() else 0)
 
     # ---- oracle state
     seq_len = np.full(B, max_in - 1, dtype=np.int64)
@@ -82,7 +83,11 @@ def _run_steps(lib, cuda, B, V, Vp, max_in, out_len, lens, top_k, top_p, tempera
             if finished[b]:
                 out_ids[step, b] = end_id
                 continue
-            tok, val = S.topk_sampling_row(lg[b], int(ks[b]), ps[b], rngs[b], max_top_k, want_probs)
+            if int(ks[b]) == 0:
+                pr = lg[b] if want_probs else S.softmax_probs(lg[b:b + 1])[0]
+                tok, val = S.topp_sampling_row(pr, ps[b], rngs[b])
+            else:
+                tok, val = S.topk_sampling_row(lg[b], int(ks[b]), ps[b], rngs[b], max_top_k, want_probs)
             out_ids[step, b] = tok
             if want_probs:
                 cum[b] += np.float32(np.log(val))
@@ -178,3 +183,35 @@ def test_optional_last_tokens_and_stop_words(lib, cuda):
             lg[1, 13] = 40.0
         return lg
     _run_steps(lib, cuda, B, V, V, 4, 6, [4, 3], 1, 0.0, 1.0, 1.0, 0, 1, fn, optional_last=optional_last, stop_words=stop)
+
+
+@pytest.mark.parametrize("p", [0.3, 0.9, 1.0])
+@pytest.mark.parametrize("want_probs", [False, True])
+def test_pure_top_p_sampling(lib, cuda, p, want_probs):
+    """top_k = 0, top_p > 0: nucleus sampling (TopPSamplingLayer) -- ids exact against the oracle's sorted walk."""
+    B, V, Vp = 3, 1000, 1008
+    _run_steps(lib, cuda, B, V, Vp, 4, 24, [4, 2, 3], [0], [p], [1.0], [1.0], [11, 12, 13], want_probs,
+               _random_logits(B, Vp, scale=2.0, seed=int(p * 10)))
+
+
+def test_top_p_head_shortcut_and_mixed_batch(lib, cuda):
+    """Peaked rows take the largest probability directly (topp_beam_topk_kernel); top-k and top-p rows share a batch."""
+    B, V, Vp = 4, 512, 512
+
+    def logits(step):
+        lg = _random_logits(B, Vp, scale=1.0, seed=100)(step)
+        lg[0, (7 * step) % V] = 30.0          # row 0: one token holds ~all the mass
+        return lg
+    _run_steps(lib, cuda, B, V, Vp, 3, 16, [3, 3, 1, 2], [0, 5, 0, 1], [0.8, 0.9, 0.95, 0.0], [1.0, 0.7, 1.3, 1.0], [1.0, 1.2, 1.0, 1.0],
+               [1, 2, 3, 4], True, logits)
+
+
+def test_top_p_ties_follow_id_order(lib, cuda):
+    """Equal probabilities are walked in ascending id order (the reference's radix sort is stable)."""
+    B, V, Vp = 2, 64, 64
+
+    def logits(step):
+        lg = np.zeros((B, Vp), dtype=np.float32)      # uniform rows: every prefix sum is a tie group
+        lg[1, :8] = 1.0
+        return lg
+    _run_steps(lib, cuda, B, V, Vp, 2, 20, [2, 2], [0], [0.9], [1.0], [1.0], [5, 6], False, logits)
