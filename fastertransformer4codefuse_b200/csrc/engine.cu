@@ -24,6 +24,7 @@
 #include "decode_mega.cuh"
 
 namespace ftcf {
+int skinny_reserve_scratch();   // gemm_skinny.cu: split-K scratch must exist before the decode step is captured into a graph
 
 // ------------------------------------------------------------------------------------------------ NCCL (dlopen)
 typedef struct ncclComm* ncclComm_t;
@@ -430,6 +431,7 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
         }
     }
     if (status == FTCF_OK) status = e->gbar.ensure(256);
+    if (status == FTCF_OK) status = skinny_reserve_scratch();
     if (status == FTCF_OK && e->opt_mega != 0) status = mega_prepare(e);
     if (status == FTCF_OK && t > 1) {
         if (!nccl_unique_id) { set_error("create: tensor_para_size %d needs an NCCL unique id", t); status = FTCF_ERR_INVALID; }

@@ -15,6 +15,8 @@
 //     fragments come from ONE contiguous 16-byte piece of a weight row (no shuffles, no transposes);
 //   * cross-warp (split-k inside the CTA) reduction through shared memory in a fixed order -> deterministic;
 //   * epilogue: per-column scale (fp32), bias, tanh-GELU, fp16 (or fp32 logits) store.
+#include <algorithm>
+
 #include "tma_utils.cuh"
 
 namespace ftcf {
@@ -48,7 +50,8 @@ __device__ __forceinline__ uint32_t u4_get(const uint4& v, int i)
 
 // tunables (ftcf_set_tunable): how many CTAs one launch aims for (all of them co-resident, so HBM is shared evenly and the
 // next kernel's CTAs fit beside them) -- see launch_skinny.
-std::atomic<int> g_sk_target_ctas{296};
+std::atomic<int> g_sk_target_ctas{0};    // 0: automatic (see skinny_shape)
+std::atomic<int> g_sk_ksplit{0};         // 1: split k when a launch has fewer than half as many CTAs as slots (measured: no gain, off)
 std::atomic<int> g_sk_carveout{1};       // 1: ask for the maximum shared-memory carveout (3 CTAs per SM fit)
 std::atomic<int> g_sk_pf_ahead{0};       // stages (16 KB each) of its OWN stream a producer keeps prefetched in L2 beyond the shared-memory ring
 std::atomic<int> g_sk_prefetch_rows{0};  // rows of each NEXT-kernel CTA slice that a finishing CTA prefetches into L2; measured on B200: it does not pay (gcb_2.log), so 0 = off
@@ -83,11 +86,15 @@ struct SkPro {
 //                   128-byte swizzle), converts
 //                   u8 -> fp16 in registers and issues mma.sync.m16n8k16 against the token fragments (read through L1);
 //   end of a pass : the four k-step warps of a tile are summed through shared memory in a fixed order, epilogue, store.
+// Split-K (gridDim.z > 1; used when a GEMM has fewer row tiles than the GPU has CTA slots, i.e. n <= ~9000): CTA (x, y, z)
+// streams k-chunk z of its rows and stores fp32 partial sums; the LAST CTA to arrive for a row tile (ticket counter) adds the
+// gridDim.z partials in the fixed order 0, 1, ... and runs the epilogue -- deterministic, no second launch.
 template <typename WT, int MT, int EPI, bool PRO = false>
 __global__ void __launch_bounds__(sk::THREADS, (MT <= 2 ? 2 : 1))
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, const __half* __restrict__ x, const __half* __restrict__ scale,
                    const __half* __restrict__ bias, void* __restrict__ y, int m, int n, int k, int ldy, int act, int rows_per_cta,
-                   const uint8_t* __restrict__ next_w, int next_n, int next_row_bytes, int next_rows_per_cta, int next_pf_rows, int pf_ahead)
+                   const uint8_t* __restrict__ next_w, int next_n, int next_row_bytes, int next_rows_per_cta, int next_pf_rows, int pf_ahead,
+                   float* __restrict__ part, int* __restrict__ tickets)
 {
     using namespace sk;
     constexpr int EPC = 16 / sizeof(WT);   // k-elements per 16-byte chunk
@@ -105,9 +112,13 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(n, r0 + rows_per_cta);
     const int m0 = blockIdx.y * NT;
     const int row_bytes = k * (int)sizeof(WT);
-    const int chunks = (row_bytes + CHUNK - 1) / CHUNK;
+    const int chunks_all = (row_bytes + CHUNK - 1) / CHUNK;
+    const int cps = (chunks_all + (int)gridDim.z - 1) / (int)gridDim.z;          // chunks per k-split
+    const int kc0 = (int)blockIdx.z * cps, kc1 = min(chunks_all, kc0 + cps);
+    const int chunks = max(kc1 - kc0, 0);
     const int passes = (r1 - r0 + ROWS - 1) / ROWS;
     const int total = passes * chunks;       // stages this CTA streams
+    __shared__ int s_last;
 
     pdl_launch_dependents();
     if (threadIdx.x == 0) {
@@ -132,14 +143,14 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
                     // kernel): one burst of L2 prefetches for the stages that follow the ring.  (A rolling window was measured
                     // to cost steady-state bandwidth: every byte then crosses L2 twice.)
                     for (int pf_i = STAGES; pf_i < min(total, STAGES + pf_ahead); ++pf_i) {
-                        const int ppass = pf_i / chunks, pkc = pf_i % chunks;
+                        const int ppass = pf_i / chunks, pkc = kc0 + pf_i % chunks;
                         const int pn = min(4, (row_bytes - pkc * CHUNK) / 128);
                         for (int j = 0; j < pn; ++j) prefetch_2d(&map_w, (pkc * CHUNK + j * 128) / (int)sizeof(WT), r0 + ppass * ROWS);
                     }
                 }
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
-                const int pass = i / chunks, kc = i % chunks;
+                const int pass = i / chunks, kc = kc0 + i % chunks;
                 const int nsub = min(4, (row_bytes - kc * CHUNK) / 128);     // 128-byte k-steps in this chunk
                 mbar_wait(&bar_empty[s], ph ^ 1);
                 mbar_arrive_expect_tx(&bar_full[s], (uint32_t)(nsub * SUB_BYTES));
@@ -251,12 +262,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
     }
     int i = 0;
     for (int pass = 0; pass < passes; ++pass) {
-        float acc[MT][4];
+        float acc[MT][4], acc1[MT][4];       // two accumulator chains: consecutive MMAs do not wait for each other
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[mt][j] = 0.f;
-        for (int kc = 0; kc < chunks; ++kc, ++i) {
+            for (int j = 0; j < 4; ++j) acc[mt][j] = acc1[mt][j] = 0.f;
+        for (int kc = kc0; kc < kc1; ++kc, ++i) {
             const int s = i % STAGES;
             const uint32_t ph = (i / STAGES) & 1;
             const bool active = (kc * CHUNK + ks * 128) < row_bytes;     // last chunk of a row may be short
@@ -300,8 +311,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
                             a3 = u4_get(wv[1][c], 2 * j + 1);
                         }
 #pragma unroll
-                        for (int mt = 0; mt < MT; ++mt)
-                            mma_16816(acc[mt], a0, a1, a2, a3, u4_get(xv[mt][pi / 4], pi % 4), u4_get(xv[mt][(pi + 1) / 4], (pi + 1) % 4));
+                        for (int mt = 0; mt < MT; ++mt) {
+                            if (j & 1) mma_16816(acc1[mt], a0, a1, a2, a3, u4_get(xv[mt][pi / 4], pi % 4), u4_get(xv[mt][(pi + 1) / 4], (pi + 1) % 4));
+                            else mma_16816(acc[mt], a0, a1, a2, a3, u4_get(xv[mt][pi / 4], pi % 4), u4_get(xv[mt][(pi + 1) / 4], (pi + 1) % 4));
+                        }
                     }
             } else {
                 __syncwarp();
@@ -311,6 +324,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
         // ---- sum the four k-step warps of each tile (fixed order), epilogue, store
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[mt][j] += acc1[mt][j];
             const int tok = mt * 8 + 2 * t;
             red[cw][tok][g] = acc[mt][0];
             red[cw][tok + 1][g] = acc[mt][1];
@@ -319,14 +334,46 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int p0 = r0 + pass * ROWS;
-        for (int o = threadIdx.x - 32; o < ROWS * NT; o += 256) {
+        const int S = (int)gridDim.z;
+        bool finish = true;
+        if (S > 1) {
+            // publish this k-split's partial tile, take a ticket; only the last arriver goes on
+            for (int o = threadIdx.x - 32; o < ROWS * NT; o += 256) {
+                const int f = o % ROWS, tok = o / ROWS;
+                const int col = p0 + f, row = m0 + tok;
+                if (col >= r1 || row >= m) continue;
+                const int tl = f >> 4, fl = f & 15;
+                float v = red[tl * 4 + 0][tok][fl] + red[tl * 4 + 1][tok][fl];
+                v += red[tl * 4 + 2][tok][fl];
+                v += red[tl * 4 + 3][tok][fl];
+                part[((size_t)blockIdx.z * m + row) * n + col] = v;
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 32) {
+                const int tile_id = (p0 / ROWS) * (int)gridDim.y + (int)blockIdx.y;
+                const int old = atomicAdd(&tickets[tile_id], 1);
+                s_last = old == S - 1;
+                if (old == S - 1) tickets[tile_id] = 0;      // self-resetting for the next launch that uses this slot
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            finish = s_last != 0;
+            if (finish) __threadfence();
+        }
+        for (int o = threadIdx.x - 32; o < ROWS * NT && finish; o += 256) {
             const int f = o % ROWS, tok = o / ROWS;
             const int col = p0 + f, row = m0 + tok;
             if (col >= r1 || row >= m) continue;
             const int tl = f >> 4, fl = f & 15;
-            float v = red[tl * 4 + 0][tok][fl] + red[tl * 4 + 1][tok][fl];
-            v += red[tl * 4 + 2][tok][fl];
-            v += red[tl * 4 + 3][tok][fl];
+            float v;
+            if (S > 1) {
+                v = __ldcg(&part[(size_t)row * n + col]);
+                for (int z = 1; z < S; ++z) v += __ldcg(&part[((size_t)z * m + row) * n + col]);
+            } else {
+                v = red[tl * 4 + 0][tok][fl] + red[tl * 4 + 1][tok][fl];
+                v += red[tl * 4 + 2][tok][fl];
+                v += red[tl * 4 + 3][tok][fl];
+            }
             if constexpr (EPI == EPI_W8) {
                 v *= __half2float(scale[col]);
                 if (bias != nullptr) v += __half2float(bias[col]);
@@ -348,13 +395,54 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
 
 FTCF_TRACE_INSTALLER(trace_install_gemm_skinny)
 
-static int skinny_rows_per_cta(int n)
+// ---- launch shape: how many CTAs, how many 32-row passes each, how many k-splits
+// A CTA's consumer pipeline sustains ~20-25 GB/s (measured: 148 CTAs alone reach 3.7 TB/s, 296 reach 5.7 TB/s), so a launch
+// needs at least two CTAs on every SM, all co-resident and with equal work: `slots` = CTAs that fit at once (3 per SM for the
+// one-token-group int8 / fp16 kernel, 2 otherwise); GEMMs with few row tiles (n = 5120: 160) are split along k.
+struct SkShape {
+    int rows_per_cta, ctas_x, ksplit;
+};
+static SkShape skinny_shape(int n, int k_bytes, int m_groups, bool three_per_sm)
 {
-    // every CTA gets the same whole number of 32-row passes; all CTAs of the launch are co-resident (<= target), so the
-    // weight stream is shared evenly by HBM even when the CTA count is not a multiple of the SM count
+    const int forced = g_sk_target_ctas.load(std::memory_order_relaxed);
+    (void)three_per_sm;   // 3 CTAs per SM was measured slower: the block scheduler then loads the SMs unevenly (240 CTAs: 3 + 3 + ... )
+    const int slots = forced > 0 ? forced : 296;
     const int tiles = ceil_div(n, sk::ROWS);
-    const int passes = ceil_div(tiles, g_sk_target_ctas.load(std::memory_order_relaxed));
-    return passes * sk::ROWS;
+    const int passes = ceil_div(tiles * m_groups, slots);
+    SkShape sh;
+    sh.rows_per_cta = passes * sk::ROWS;
+    sh.ctas_x = ceil_div(n, sh.rows_per_cta);
+    sh.ksplit = 1;
+    const int chunks = ceil_div(k_bytes, sk::CHUNK);
+    if (g_sk_ksplit.load(std::memory_order_relaxed) != 0 && passes == 1) {
+        int s2 = slots / (sh.ctas_x * m_groups);
+        s2 = std::min(s2, std::min(4, chunks / 5));          // at least 5 stages per CTA
+        if (s2 >= 2) sh.ksplit = s2;
+    }
+    return sh;
+}
+
+// split-K scratch: a small pool of (partials, tickets) slots handed out round-robin, so that GEMMs running concurrently on two
+// streams (FFN2 and O of one layer) never share one.  Reserved up front: cudaMalloc is not allowed during stream capture.
+namespace {
+constexpr int kPoolSlots = 8;
+constexpr size_t kPartElems = (size_t)4 * 32 * 9472;     // ksplit x m x n
+constexpr int kTicketsPerSlot = 4096;
+float* g_pool_part = nullptr;
+int* g_pool_tickets = nullptr;
+std::atomic<unsigned> g_pool_next{0};
+}  // namespace
+int skinny_reserve_scratch()
+{
+    if (g_pool_part != nullptr) return FTCF_OK;
+    float* pp = nullptr;
+    int* tt = nullptr;
+    FTCF_CUDA_CHECK(cudaMalloc(&pp, kPoolSlots * kPartElems * sizeof(float)));
+    FTCF_CUDA_CHECK(cudaMalloc(&tt, (size_t)kPoolSlots * kTicketsPerSlot * sizeof(int)));
+    FTCF_CUDA_CHECK(cudaMemset(tt, 0, (size_t)kPoolSlots * kTicketsPerSlot * sizeof(int)));
+    g_pool_tickets = tt;
+    g_pool_part = pp;
+    return FTCF_OK;
 }
 
 template <typename WT, int EPI>
@@ -365,7 +453,28 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
     FTCF_REQUIRE(k % (8 * EPC) == 0, FTCF_ERR_UNSUPPORTED, "skinny gemm: k=%d must be a multiple of %d", k, 8 * EPC);
     FTCF_REQUIRE(m > 0 && n > 0, FTCF_ERR_INVALID, "skinny gemm: empty problem m=%d n=%d", m, n);
     const int mt = m >= 25 ? 4 : ceil_div(m, 8);
-    const int rows_per_cta = skinny_rows_per_cta(n);
+    const int m_groups = ceil_div(m, 8 * mt);
+    SkShape sh = skinny_shape(n, k * (int)sizeof(WT), m_groups, mt == 1 && pro == nullptr);
+    float* part = nullptr;
+    int* tickets = nullptr;
+    if (sh.ksplit > 1) {
+        if (g_pool_part == nullptr) {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+                const int rc = skinny_reserve_scratch();
+                if (rc != FTCF_OK) return rc;
+            }
+        }
+        const bool fits = g_pool_part != nullptr && (size_t)sh.ksplit * m * n <= kPartElems && ceil_div(n, sk::ROWS) * m_groups <= kTicketsPerSlot;
+        if (!fits) {
+            sh.ksplit = 1;
+        } else {
+            const unsigned slot = g_pool_next.fetch_add(1) % kPoolSlots;
+            part = g_pool_part + (size_t)slot * kPartElems;
+            tickets = g_pool_tickets + (size_t)slot * kTicketsPerSlot;
+        }
+    }
+    const int rows_per_cta = sh.rows_per_cta;
     const uint8_t* next_w = nullptr;
     int next_n = 0, next_row_bytes = 0, next_rpc = 1;
     const int next_pf = g_sk_prefetch_rows.load(std::memory_order_relaxed);
@@ -374,9 +483,9 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
         next_w = static_cast<const uint8_t*>(next->w);
         next_n = next->n;
         next_row_bytes = next->row_bytes;
-        next_rpc = skinny_rows_per_cta(next->n);
+        next_rpc = skinny_shape(next->n, next->row_bytes, 1, true).rows_per_cta;
     }
-    const dim3 grid(ceil_div(n, rows_per_cta), ceil_div(m, 8 * mt));
+    const dim3 grid(sh.ctas_x, m_groups, sh.ksplit);
     const dim3 block(sk::THREADS);
     size_t smem = (size_t)sk::STAGES * sk::STAGE_BYTES + 1024;
     SkPro prov{};
@@ -407,7 +516,7 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
             configured = smem;                                                                                          \
         }                                                                                                               \
         if (err == cudaSuccess)                                                                                         \
-            err = launch_pdl(gemm_skinny_kernel<WT, MT_, EPI, PRO_>, grid, block, smem, st, mw, prov, xs, sc, bs, y, m, n, k, ldy, act, rows_per_cta, next_w, next_n, next_row_bytes, next_rpc, next_pf, pf_ahead); \
+            err = launch_pdl(gemm_skinny_kernel<WT, MT_, EPI, PRO_>, grid, block, smem, st, mw, prov, xs, sc, bs, y, m, n, k, ldy, act, rows_per_cta, next_w, next_n, next_row_bytes, next_rpc, next_pf, pf_ahead, part, tickets); \
     } while (0)
 #define FTCF_SK(MT_) FTCF_SK_(MT_, false)
     if (pro != nullptr) {

@@ -67,22 +67,25 @@ int main(int argc, char** argv)
         printf("%-58s %8.3f ms  %8.1f GB/s\n", name, ms, bytes / (ms * 1e-3) / 1e9);
     };
 
-    // per-shape: 40 launches of ONE shape (different weights each), graph + PDL -> GB/s of that shape in a dependent chain
-    for (int ctas : {296, 444, 592})
-        for (int i = 0; i < 4; ++i) {
+    // per-shape: 40 launches of ONE shape (different weights each), graph + PDL -> GB/s of that shape in a dependent chain.
+    // The extra shapes test the per-SM balance theory: n = 148*32 and 296*32 rows give every SM the same number of CTAs.
+    const int tn[] = {15360, 5120, 20480, 5120, 4736, 9472, 4736, 18944, 14208};
+    const int tk[] = {5120, 5120, 5120, 20480, 20480, 20480, 5120, 5120, 5120};
+    for (int ctas : {296})
+        for (int i = 0; i < 9; ++i) {
             ftcf_set_tunable("skinny_prefetch_rows", 0);
             ftcf_set_tunable("skinny_pf_ahead", 0);
             ftcf_set_tunable("pdl", 1);
             ftcf_set_tunable("skinny_target_ctas", ctas);
-            const size_t bytes = (size_t)ks[i] * ns[i];
+            const size_t bytes = (size_t)tk[i] * tn[i];
             cudaGraph_t g;
             cudaGraphExec_t ge;
             CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            for (int l = 0; l < L; ++l) FK(ftcf_gemm_w8a16(x, w + (size_t)l * total, scale, nullptr, y, m, ns[i], ks[i], 0, 1, st));
+            for (int l = 0; l < L; ++l) FK(ftcf_gemm_w8a16(x, w + (size_t)l * total, scale, nullptr, y, m, tn[i], tk[i], 0, 1, st));
             CK(cudaStreamEndCapture(st, &g));
             CK(cudaGraphInstantiate(&ge, g, 0));
             char name[128];
-            snprintf(name, sizeof(name), "m=%d ctas=%d: 40 x (n=%d, k=%d) chain, graph+pdl", m, ctas, ns[i], ks[i]);
+            snprintf(name, sizeof(name), "m=%d ctas=%d: 40 x (n=%d, k=%d) chain, graph+pdl", m, ctas, tn[i], tk[i]);
             timed(name, [&]() { CK(cudaGraphLaunch(ge, st)); }, (double)bytes * L, 10);
             cudaGraphExecDestroy(ge);
             cudaGraphDestroy(g);
