@@ -48,7 +48,7 @@ class PrefetchHint(C.Structure):
 
 class LnPrologue(C.Structure):
     _fields_ = [("x", C.c_void_p), ("add_ffn", C.c_void_p), ("add_attn", C.c_void_p), ("add_bias", C.c_void_p),
-                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("x_out", C.c_void_p), ("eps", C.c_float)]
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("x_out", C.c_void_p), ("eps", C.c_float), ("cta_hint", C.c_int32)]
 
 
 class GptNeoXConfig(C.Structure):
@@ -117,6 +117,7 @@ SIGNATURES = {
     "ftcf_add_bias_residual": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p]),
     "ftcf_embedding_lookup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ftcf_mmha_decode": (C.c_int, [C.POINTER(MmhaParams), C.c_void_p]),
+    "ftcf_mmha_prefetch_cache": (C.c_int, [C.POINTER(MmhaParams), C.c_void_p]),
     "ftcf_mmha_choose_splits": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "ftcf_prefill_qkv_rotary_scatter": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p]),
     "ftcf_prefill_attention": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 5 + [C.c_float, C.c_void_p]),

@@ -287,6 +287,28 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
     }
 }
 
+// L2 prefetch of the cache rows one decode-attention launch will read (every valid slot < seq_len of every sequence and head),
+// launched on a side stream at the START of the layer: the rows travel while the QKV GEMM streams its weights, and the
+// attention kernel -- a chain of dependent load rounds -- then runs on L2 hits.  evict_last so the weight stream (evict_first)
+// does not push them out again.  Reads request state only (constant within a step); touches no data.
+__global__ void __launch_bounds__(256) kv_prefetch_kernel(const __half* __restrict__ k_cache, const __half* __restrict__ v_cache,
+                                                          const int32_t* __restrict__ seq_len, const int32_t* __restrict__ input_len,
+                                                          const uint8_t* __restrict__ finished, int heads, int dh, int max_len, int max_in)
+{
+    const int h = blockIdx.x, b = blockIdx.y;
+    if (finished != nullptr && finished[b]) return;
+    const int tlen = seq_len[b], in_len = input_len[b];
+    const size_t base = ((size_t)b * heads + h) * (size_t)max_len * dh;
+    const int lines = (dh * 2) / 128;                         // 128-byte lines per row
+    const int per_row = 2 * lines;                            // K and V
+    for (int i = threadIdx.x; i < tlen * per_row; i += blockDim.x) {
+        const int pos = i / per_row, r = i % per_row;
+        if (pos >= in_len && pos < max_in) continue;
+        const __half* src = (r < lines ? k_cache : v_cache) + base + (size_t)pos * dh;
+        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(reinterpret_cast<const char*>(src) + (r % lines) * 128));
+    }
+}
+
 FTCF_TRACE_INSTALLER(trace_install_attention)
 
 // ---------------------------------------------------------------- prefill: bias + rotary + scatter
@@ -440,6 +462,16 @@ extern "C" int ftcf_mmha_choose_splits(int batch, int heads, int max_len)
     if (splits < need) splits = need;
     if (splits < 1) splits = 1;
     return splits;
+}
+
+extern "C" int ftcf_mmha_prefetch_cache(const ftcf_mmha_params* p, void* stream)
+{
+    FTCF_REQUIRE(p != nullptr && p->batch > 0 && p->heads > 0, FTCF_ERR_INVALID, "mmha prefetch: bad params");
+    kv_prefetch_kernel<<<dim3(p->heads, p->batch), 256, 0, as_stream(stream)>>>(
+        static_cast<const __half*>(p->k_cache), static_cast<const __half*>(p->v_cache), p->seq_len, p->input_len, p->finished, p->heads,
+        p->dh, p->max_len, p->max_input_len);
+    FTCF_LAUNCH_CHECK();
+    return FTCF_OK;
 }
 
 extern "C" int ftcf_mmha_decode(const ftcf_mmha_params* p, void* stream)

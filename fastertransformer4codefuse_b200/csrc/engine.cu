@@ -161,6 +161,8 @@ struct ftcf_gptneox {
     cudaEvent_t caller_ev = nullptr;
     cudaStream_t side = nullptr;            // second branch of the decode layer (FFN) so that it overlaps the attention branch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side2 = nullptr;           // KV-cache L2 prefetch of the decode layer
+    cudaEvent_t ev_join2 = nullptr;
     int h = 0, Hl = 0, hl = 0, inter_l = 0, Vp = 0, Vl = 0, t = 1, rank = 0;
     std::vector<LayerW> layers;
     const __half *wte = nullptr, *lnf_g = nullptr, *lnf_b = nullptr, *lm_head = nullptr;
@@ -168,7 +170,7 @@ struct ftcf_gptneox {
     ncclComm_t comm = nullptr;
 
     // options
-    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_mega = 0;   // mega: persistent decode-step kernel (decode_mega.cu), experimental -- measured slower than the graph (profiles/)
+    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_kv_prefetch = 0, opt_pro_ctas = 148, opt_mega = 0;   // mega: persistent decode-step kernel (decode_mega.cu), experimental -- measured slower than the graph (profiles/)
 
     // request-sized buffers (grow only)
     DevBuf kv, x, x2, n1, n2, qkv, qbuf, ctx, attn, inter, ffn, logits, logits_local, logits_gather, samp_ws, small, mmha_part,
@@ -359,7 +361,9 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
         cudaEventCreateWithFlags(&e->caller_ev, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&e->side2, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
         set_error("create: cannot create the engine stream");
         delete e;
         return FTCF_ERR_CUDA;
@@ -474,6 +478,8 @@ extern "C" void ftcf_gptneox_destroy(ftcf_gptneox* e)
     if (e->caller_ev) cudaEventDestroy(e->caller_ev);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->ev_join2) cudaEventDestroy(e->ev_join2);
+    if (e->side2) cudaStreamDestroy(e->side2);
     if (e->side) cudaStreamDestroy(e->side);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -488,6 +494,8 @@ extern "C" int ftcf_gptneox_set_option(ftcf_gptneox* e, const char* name, int va
     else if (n == "step_timing") e->opt_step_timing = value;
     else if (n == "two_branch") e->opt_two_branch = value;
     else if (n == "fused_ln") e->opt_fused_ln = value;
+    else if (n == "kv_prefetch") e->opt_kv_prefetch = value;
+    else if (n == "pro_ctas") e->opt_pro_ctas = value;
     else if (n == "mega") {
         e->opt_mega = value;
         if (value != 0) FTCF_TRY(mega_prepare(e));
@@ -552,6 +560,8 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
         auto prologue = [&](int l, const __half* g, const __half* b, bool store) {
             ftcf_ln_prologue pro{};
             pro.gamma = g; pro.beta = b; pro.eps = c.layernorm_eps;
+            // QKV and FFN1 start together: half of the SM slots each (measured: QKV otherwise queues behind FFN1's CTAs for ~25 us)
+            pro.cta_hint = (l < c.layer_num && e->opt_two_branch) ? e->opt_pro_ctas : 0;
             if (l == 0) {
                 pro.x = xb[0];
             } else {
@@ -572,6 +582,23 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
                 FTCF_CUDA_CHECK(cudaEventRecord(e->ev_fork, st));
                 FTCF_CUDA_CHECK(cudaStreamWaitEvent(sb, e->ev_fork, 0));
             }
+            ftcf_mmha_params mp{};
+            mp.qkv = e->qkv.p;
+            mp.qkv_bias = lw.qkv_b;
+            mp.k_cache = e->kv.as<__half>() + (size_t)(2 * l) * per_layer;
+            mp.v_cache = e->kv.as<__half>() + (size_t)(2 * l + 1) * per_layer;
+            mp.ctx = e->ctx.p;
+            mp.seq_len = s.seq_len; mp.input_len = s.input_len; mp.pad_count = s.pad_count; mp.finished = s.finished; mp.step = s.step;
+            mp.partial = e->mmha_part.as<float>(); mp.counters = s.counters;
+            mp.batch = B; mp.heads = e->Hl; mp.dh = dh; mp.rotary_dim = c.rotary_embedding_dim;
+            mp.max_len = max_len; mp.max_input_len = S; mp.splits = splits;
+            mp.inv_sqrt_dh = 1.f / std::sqrt((float)dh);
+            const bool kvpf = e->opt_two_branch && e->opt_kv_prefetch;
+            if (kvpf) {   // this layer's cache rows start travelling to L2 now, while the GEMMs stream their weights
+                FTCF_CUDA_CHECK(cudaStreamWaitEvent(e->side2, e->ev_fork, 0));
+                FTCF_TRY(ftcf_mmha_prefetch_cache(&mp, e->side2));
+                FTCF_CUDA_CHECK(cudaEventRecord(e->ev_join2, e->side2));
+            }
             const ftcf_ln_prologue p2 = prologue(l, lw.ln2_g, lw.ln2_b, false);
             if (w8) {
                 FTCF_TRY(ftcf_gemm_w8a16_ln(&p2, static_cast<const uint8_t*>(lw.w[2]), lw.scale[2], lw.ffn1_b, e->inter.p, B, e->inter_l, e->h, 1, sb));
@@ -584,21 +611,11 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
             const ftcf_ln_prologue p1 = prologue(l, lw.ln1_g, lw.ln1_b, true);
             if (w8) FTCF_TRY(ftcf_gemm_w8a16_ln(&p1, static_cast<const uint8_t*>(lw.w[0]), lw.scale[0], nullptr, e->qkv.p, B, 3 * e->hl, e->h, 0, st));
             else FTCF_TRY(ftcf_gemm_f16_ln(&p1, lw.w[0], nullptr, e->qkv.p, B, 3 * e->hl, e->h, 3 * e->hl, 0, 0, st));
-            ftcf_mmha_params mp{};
-            mp.qkv = e->qkv.p;
-            mp.qkv_bias = lw.qkv_b;
-            mp.k_cache = e->kv.as<__half>() + (size_t)(2 * l) * per_layer;
-            mp.v_cache = e->kv.as<__half>() + (size_t)(2 * l + 1) * per_layer;
-            mp.ctx = e->ctx.p;
-            mp.seq_len = s.seq_len; mp.input_len = s.input_len; mp.pad_count = s.pad_count; mp.finished = s.finished; mp.step = s.step;
-            mp.partial = e->mmha_part.as<float>(); mp.counters = s.counters;
-            mp.batch = B; mp.heads = e->Hl; mp.dh = dh; mp.rotary_dim = c.rotary_embedding_dim;
-            mp.max_len = max_len; mp.max_input_len = S; mp.splits = splits;
-            mp.inv_sqrt_dh = 1.f / std::sqrt((float)dh);
             FTCF_TRY(ftcf_mmha_decode(&mp, st));
             if (w8) FTCF_TRY(ftcf_gemm_w8a16(e->ctx.p, static_cast<const uint8_t*>(lw.w[1]), lw.scale[1], nullptr, attn[l & 1], B, e->h, e->hl, 0, 1, st));
             else FTCF_TRY(ftcf_gemm_f16(e->ctx.p, lw.w[1], nullptr, attn[l & 1], B, e->h, e->hl, e->h, 0, 0, 1, st));
             if (e->opt_two_branch) FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join, 0));
+            if (kvpf) FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join2, 0));
         }
         // final LayerNorm (on the last layer's residual sum) as the prologue of the LM head
         const ftcf_ln_prologue pf = prologue(L, e->lnf_g, e->lnf_b, false);

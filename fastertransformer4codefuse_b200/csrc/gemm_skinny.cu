@@ -51,7 +51,9 @@ __device__ __forceinline__ uint32_t u4_get(const uint4& v, int i)
 // tunables (ftcf_set_tunable): how many CTAs one launch aims for (all of them co-resident, so HBM is shared evenly and the
 // next kernel's CTAs fit beside them) -- see launch_skinny.
 std::atomic<int> g_sk_target_ctas{0};    // 0: automatic (see skinny_shape)
+std::atomic<int> g_sk_even_rows{0};      // 1: rows per pass (TMA box height 8..32) chosen so that all co-resident CTAs get equal shares; measured: per-shape +3 %, but the extra CTAs starve the attention kernel of SM slots (decode step +20 %), so off
 std::atomic<int> g_sk_ksplit{0};         // 1: split k when a launch has fewer than half as many CTAs as slots (measured: no gain, off)
+std::atomic<int> g_sk_evict_first{1};    // weight tiles are loaded with an L2 evict_first policy
 std::atomic<int> g_sk_carveout{1};       // 1: ask for the maximum shared-memory carveout (3 CTAs per SM fit)
 std::atomic<int> g_sk_pf_ahead{0};       // stages (16 KB each) of its OWN stream a producer keeps prefetched in L2 beyond the shared-memory ring
 std::atomic<int> g_sk_prefetch_rows{0};  // rows of each NEXT-kernel CTA slice that a finishing CTA prefetches into L2; measured on B200: it does not pay (gcb_2.log), so 0 = off
@@ -76,6 +78,7 @@ struct SkPro {
     const __half *x, *add_ffn, *add_attn, *add_bias, *gamma, *beta;
     __half* x_out;
     float eps;
+    int cta_hint;
 };
 
 // Pipelined skinny GEMM.  One CTA owns the contiguous feature rows [r0, r1) and all of k.
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(sk::THREADS, (MT <= 2 ? 2 : 1))
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, const __half* __restrict__ x, const __half* __restrict__ scale,
                    const __half* __restrict__ bias, void* __restrict__ y, int m, int n, int k, int ldy, int act, int rows_per_cta,
                    const uint8_t* __restrict__ next_w, int next_n, int next_row_bytes, int next_rows_per_cta, int next_pf_rows, int pf_ahead,
-                   float* __restrict__ part, int* __restrict__ tickets)
+                   float* __restrict__ part, int* __restrict__ tickets, int evict_first, int R)
 {
     using namespace sk;
     constexpr int EPC = 16 / sizeof(WT);   // k-elements per 16-byte chunk
@@ -116,7 +119,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
     const int cps = (chunks_all + (int)gridDim.z - 1) / (int)gridDim.z;          // chunks per k-split
     const int kc0 = (int)blockIdx.z * cps, kc1 = min(chunks_all, kc0 + cps);
     const int chunks = max(kc1 - kc0, 0);
-    const int passes = (r1 - r0 + ROWS - 1) / ROWS;
+    // R = rows per pass = height of the TMA box (<= ROWS; each box still owns a 32-row slot of the stage so that the
+    // 128-byte swizzle pattern stays 1024-byte aligned): lets the host cut n into equal shares for ALL co-resident CTAs
+    const int passes = (r1 - r0 + R - 1) / R;
     const int total = passes * chunks;       // stages this CTA streams
     __shared__ int s_last;
 
@@ -134,6 +139,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
         // ================= producer =================
         if (lane == 0) {
             prefetch_map(&map_w);
+            const uint64_t pol = l2_policy_evict_first();
             // L2 prefetch window: while this CTA's consumers still wait for the previous kernel (PDL) -- and HBM would idle
             // through the kernel boundary with only the 64 KB ring requested -- the producer keeps asking L2 for the stages
             // that follow the ring, so the ring later refills at L2 latency.
@@ -145,7 +151,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
                     for (int pf_i = STAGES; pf_i < min(total, STAGES + pf_ahead); ++pf_i) {
                         const int ppass = pf_i / chunks, pkc = kc0 + pf_i % chunks;
                         const int pn = min(4, (row_bytes - pkc * CHUNK) / 128);
-                        for (int j = 0; j < pn; ++j) prefetch_2d(&map_w, (pkc * CHUNK + j * 128) / (int)sizeof(WT), r0 + ppass * ROWS);
+                        for (int j = 0; j < pn; ++j) prefetch_2d(&map_w, (pkc * CHUNK + j * 128) / (int)sizeof(WT), r0 + ppass * R);
                     }
                 }
                 const int s = i % STAGES;
@@ -153,10 +159,16 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
                 const int pass = i / chunks, kc = kc0 + i % chunks;
                 const int nsub = min(4, (row_bytes - kc * CHUNK) / 128);     // 128-byte k-steps in this chunk
                 mbar_wait(&bar_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&bar_full[s], (uint32_t)(nsub * SUB_BYTES));
-                for (int j = 0; j < nsub; ++j)
-                    load_2d(sk_smem + (size_t)s * STAGE_BYTES + j * SUB_BYTES, &map_w, &bar_full[s],
-                            (kc * CHUNK + j * 128) / (int)sizeof(WT), r0 + pass * ROWS);
+                mbar_arrive_expect_tx(&bar_full[s], (uint32_t)(nsub * R * 128));
+                if (evict_first) {
+                    for (int j = 0; j < nsub; ++j)
+                        load_2d_hint(sk_smem + (size_t)s * STAGE_BYTES + j * SUB_BYTES, &map_w, &bar_full[s],
+                                     (kc * CHUNK + j * 128) / (int)sizeof(WT), r0 + pass * R, pol);
+                } else {
+                    for (int j = 0; j < nsub; ++j)
+                        load_2d(sk_smem + (size_t)s * STAGE_BYTES + j * SUB_BYTES, &map_w, &bar_full[s],
+                                (kc * CHUNK + j * 128) / (int)sizeof(WT), r0 + pass * R);
+                }
             }
         }
         // Tail prefetch: everything this CTA needs has been requested; queue L2 prefetches for the HEAD of the next GEMM's
@@ -333,7 +345,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
             red[cw][tok + 1][g + 8] = acc[mt][3];
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int p0 = r0 + pass * ROWS;
+        const int p0 = r0 + pass * R;
+        const int pr1 = min(r1, p0 + R);          // rows of this pass that belong to this CTA
         const int S = (int)gridDim.z;
         bool finish = true;
         if (S > 1) {
@@ -341,7 +354,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
             for (int o = threadIdx.x - 32; o < ROWS * NT; o += 256) {
                 const int f = o % ROWS, tok = o / ROWS;
                 const int col = p0 + f, row = m0 + tok;
-                if (col >= r1 || row >= m) continue;
+                if (col >= pr1 || row >= m) continue;
                 const int tl = f >> 4, fl = f & 15;
                 float v = red[tl * 4 + 0][tok][fl] + red[tl * 4 + 1][tok][fl];
                 v += red[tl * 4 + 2][tok][fl];
@@ -351,7 +364,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
             __threadfence();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (threadIdx.x == 32) {
-                const int tile_id = (p0 / ROWS) * (int)gridDim.y + (int)blockIdx.y;
+                const int tile_id = (p0 / R) * (int)gridDim.y + (int)blockIdx.y;
                 const int old = atomicAdd(&tickets[tile_id], 1);
                 s_last = old == S - 1;
                 if (old == S - 1) tickets[tile_id] = 0;      // self-resetting for the next launch that uses this slot
@@ -363,7 +376,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
         for (int o = threadIdx.x - 32; o < ROWS * NT && finish; o += 256) {
             const int f = o % ROWS, tok = o / ROWS;
             const int col = p0 + f, row = m0 + tok;
-            if (col >= r1 || row >= m) continue;
+            if (col >= pr1 || row >= m) continue;
             const int tl = f >> 4, fl = f & 15;
             float v;
             if (S > 1) {
@@ -400,17 +413,29 @@ FTCF_TRACE_INSTALLER(trace_install_gemm_skinny)
 // needs at least two CTAs on every SM, all co-resident and with equal work: `slots` = CTAs that fit at once (3 per SM for the
 // one-token-group int8 / fp16 kernel, 2 otherwise); GEMMs with few row tiles (n = 5120: 160) are split along k.
 struct SkShape {
-    int rows_per_cta, ctas_x, ksplit;
+    int rows_per_cta, ctas_x, ksplit, box_rows;
 };
-static SkShape skinny_shape(int n, int k_bytes, int m_groups, bool three_per_sm)
+static SkShape skinny_shape(int n, int k_bytes, int m_groups, bool three_per_sm, int hint = 0)
 {
-    const int forced = g_sk_target_ctas.load(std::memory_order_relaxed);
+    const int forced = hint > 0 ? hint : g_sk_target_ctas.load(std::memory_order_relaxed);
     (void)three_per_sm;   // 3 CTAs per SM was measured slower: the block scheduler then loads the SMs unevenly (240 CTAs: 3 + 3 + ... )
     const int slots = forced > 0 ? forced : 296;
-    const int tiles = ceil_div(n, sk::ROWS);
-    const int passes = ceil_div(tiles * m_groups, slots);
+    // equal shares: the smallest pass count whose per-pass height fits a box (<= 32 rows, multiple of 4)
+    const int per_cta_max = std::max(1, slots / m_groups);
+    int passes = 1, R = sk::ROWS;
+    for (;; ++passes) {
+        const int want = ceil_div(n, per_cta_max * passes);        // rows per pass if every slot got an equal share
+        R = std::max(8, ((want + 3) / 4) * 4);
+        if (R <= sk::ROWS) break;
+    }
+    if (g_sk_even_rows.load(std::memory_order_relaxed) == 0) {      // old rule: whole 32-row tiles
+        const int tiles = ceil_div(n, sk::ROWS);
+        passes = ceil_div(tiles * m_groups, slots);
+        R = sk::ROWS;
+    }
     SkShape sh;
-    sh.rows_per_cta = passes * sk::ROWS;
+    sh.box_rows = R;
+    sh.rows_per_cta = passes * R;
     sh.ctas_x = ceil_div(n, sh.rows_per_cta);
     sh.ksplit = 1;
     const int chunks = ceil_div(k_bytes, sk::CHUNK);
@@ -454,7 +479,7 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
     FTCF_REQUIRE(m > 0 && n > 0, FTCF_ERR_INVALID, "skinny gemm: empty problem m=%d n=%d", m, n);
     const int mt = m >= 25 ? 4 : ceil_div(m, 8);
     const int m_groups = ceil_div(m, 8 * mt);
-    SkShape sh = skinny_shape(n, k * (int)sizeof(WT), m_groups, mt == 1 && pro == nullptr);
+    SkShape sh = skinny_shape(n, k * (int)sizeof(WT), m_groups, mt == 1 && pro == nullptr, pro != nullptr ? pro->cta_hint : 0);
     float* part = nullptr;
     int* tickets = nullptr;
     if (sh.ksplit > 1) {
@@ -465,7 +490,7 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
                 if (rc != FTCF_OK) return rc;
             }
         }
-        const bool fits = g_pool_part != nullptr && (size_t)sh.ksplit * m * n <= kPartElems && ceil_div(n, sk::ROWS) * m_groups <= kTicketsPerSlot;
+        const bool fits = g_pool_part != nullptr && (size_t)sh.ksplit * m * n <= kPartElems && ceil_div(n, sh.box_rows) * m_groups <= kTicketsPerSlot;
         if (!fits) {
             sh.ksplit = 1;
         } else {
@@ -479,6 +504,7 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
     int next_n = 0, next_row_bytes = 0, next_rpc = 1;
     const int next_pf = g_sk_prefetch_rows.load(std::memory_order_relaxed);
     const int pf_ahead = g_sk_pf_ahead.load(std::memory_order_relaxed);
+    const int evict_first = g_sk_evict_first.load(std::memory_order_relaxed);
     if (next != nullptr && next->w != nullptr && next_pf > 0 && next->row_bytes % 16 == 0) {
         next_w = static_cast<const uint8_t*>(next->w);
         next_n = next->n;
@@ -500,7 +526,7 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
     const __half* xs = static_cast<const __half*>(x);
     CUtensorMap mw;
     {
-        const int rc = make_tensor_map_2d(&mw, w, n, k, (int)sizeof(WT), sk::ROWS);
+        const int rc = make_tensor_map_2d(&mw, w, n, k, (int)sizeof(WT), sh.box_rows);
         if (rc != FTCF_OK) return rc;
     }
     const __half* sc = static_cast<const __half*>(scale);
@@ -516,7 +542,7 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
             configured = smem;                                                                                          \
         }                                                                                                               \
         if (err == cudaSuccess)                                                                                         \
-            err = launch_pdl(gemm_skinny_kernel<WT, MT_, EPI, PRO_>, grid, block, smem, st, mw, prov, xs, sc, bs, y, m, n, k, ldy, act, rows_per_cta, next_w, next_n, next_row_bytes, next_rpc, next_pf, pf_ahead, part, tickets); \
+            err = launch_pdl(gemm_skinny_kernel<WT, MT_, EPI, PRO_>, grid, block, smem, st, mw, prov, xs, sc, bs, y, m, n, k, ldy, act, rows_per_cta, next_w, next_n, next_row_bytes, next_rpc, next_pf, pf_ahead, part, tickets, evict_first, sh.box_rows); \
     } while (0)
 #define FTCF_SK(MT_) FTCF_SK_(MT_, false)
     if (pro != nullptr) {
@@ -562,6 +588,7 @@ static SkPro to_skpro(const ftcf_ln_prologue& p)
     r.beta = static_cast<const __half*>(p.beta);
     r.x_out = static_cast<__half*>(p.x_out);
     r.eps = p.eps;
+    r.cta_hint = p.cta_hint;
     return r;
 }
 int gemm_w8a16_skinny_ln(const ftcf_ln_prologue& pro, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n, int k,

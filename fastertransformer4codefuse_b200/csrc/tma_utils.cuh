@@ -53,6 +53,22 @@ __device__ __forceinline__ void load_2d(void* smem_dst, const CUtensorMap* map, 
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// same, with an L2 cache policy (createpolicy): weights are read once per token -- evict_first keeps them from flushing the
+// activations and the KV rows that were prefetched for the attention kernel
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+        : "memory");
+}
 // L2 prefetch of one box of the tensor map (no shared-memory destination, no barrier)
 __device__ __forceinline__ void prefetch_2d(const CUtensorMap* map, int c0, int c1)
 {

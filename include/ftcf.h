@@ -111,6 +111,8 @@ typedef struct {
     const void *x, *add_ffn, *add_attn, *add_bias, *gamma, *beta;   /* fp16: [m,k] [m,k] [m,k] [k] [k] [k] */
     void* x_out;                                                    /* [m,k] fp16 or NULL; must not alias x */
     float eps;
+    int32_t cta_hint;   /* 0: automatic; > 0: CTAs this launch should aim for (the engine gives the two GEMMs that start a layer
+                           together half of the SM slots each, so that neither queues behind the other) */
 } ftcf_ln_prologue;
 int ftcf_gemm_w8a16_ln(const ftcf_ln_prologue* pro, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m,
                        int n, int k, int act, void* stream);
@@ -158,6 +160,9 @@ typedef struct {
     float inv_sqrt_dh;
 } ftcf_mmha_params;
 int ftcf_mmha_decode(const ftcf_mmha_params* p, void* stream);
+/* Optional companion of ftcf_mmha_decode: L2 prefetch of the cache rows that launch will read (same params; only the cache
+ * pointers, lengths and flags are used).  Meant for a side stream at the start of the layer; never changes results. */
+int ftcf_mmha_prefetch_cache(const ftcf_mmha_params* p, void* stream);
 /* Scratch sizing / split choice for ftcf_mmha_decode. */
 int ftcf_mmha_choose_splits(int batch, int heads, int max_len);
 
