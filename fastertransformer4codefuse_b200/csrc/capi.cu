@@ -38,7 +38,7 @@ int gemm_w8a16_tcgen05(const void* x, const uint8_t* w_nk, const void* scale, co
 int gemm_f16_tcgen05(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
                      int out_f32, cudaStream_t st);
 bool gemm_tcgen05_supported(int m, int n, int k, int elem_bytes);
-extern std::atomic<int> g_mmha_pdl, g_mmha_prefetch, g_sk_carveout, g_sk_ksplit, g_sk_evict_first, g_sk_even_rows;
+extern std::atomic<int> g_mmha_pdl, g_mmha_prefetch, g_sk_carveout, g_sk_ksplit, g_sk_evict_first, g_sk_even_rows, g_tc_ksplit;
 extern std::atomic<int> g_sk_target_ctas, g_sk_prefetch_rows, g_sk_pf_ahead, g_mega_dbg, g_mega_ns, g_mega_inflight;
 
 }  // namespace ftcf
@@ -58,6 +58,7 @@ extern "C" int ftcf_set_tunable(const char* name, int value)
     else if (n == "skinny_ksplit") g_sk_ksplit.store(value);
     else if (n == "skinny_evict_first") g_sk_evict_first.store(value);
     else if (n == "skinny_even_rows") g_sk_even_rows.store(value);
+    else if (n == "tc_ksplit") g_tc_ksplit.store(value);
     else if (n == "skinny_prefetch_rows") { FTCF_REQUIRE(value >= 0, FTCF_ERR_INVALID, "skinny_prefetch_rows %d", value); g_sk_prefetch_rows.store(value); }
     else if (n == "skinny_pf_ahead") g_sk_pf_ahead.store(value);
     else if (n == "mmha_pdl") g_mmha_pdl.store(value);
@@ -134,7 +135,7 @@ extern "C" int ftcf_device_check(void)
 
 // m at or below which the streaming (skinny) kernel is used in auto mode; above it the tcgen05 kernel takes over
 // when the shape is one it supports.
-static constexpr int kSkinnyMaxM = 32;
+static constexpr int kSkinnyMaxM = 11;   // measured (decode step, 13B int8): batch 8 skinny 5.4 vs tcgen05 6.9 ms; batch 16: 8.7 vs 8.1; batch 32: 15.1 vs 12.3
 
 extern "C" int ftcf_gemm_w8a16_ex(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n,
                                   int k, int act, int impl, const ftcf_prefetch_hint* next, void* stream)

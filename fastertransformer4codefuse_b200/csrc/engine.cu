@@ -650,13 +650,15 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
             FTCF_TRY(run_layer(e, l, B, attn));
         }
     }
+    // the LM head stays on the streaming kernel up to 32 rows (1 GB of fp16 weights, 6.9 TB/s there)
+    const int lm_impl = e->opt_gemm_impl == 2 ? (B <= 32 ? 1 : 0) : (e->opt_gemm_impl == 0 && B <= 32 ? 1 : e->opt_gemm_impl);
     // final LN on x (decode) -- for the first generated token the caller has put the prefill's last-token rows in x
     FTCF_TRY(ftcf_layernorm(e->x.p, e->lnf_g, e->lnf_b, e->n1.p, B, e->h, c.layernorm_eps, st));
     if (e->t == 1) {
-        FTCF_TRY(ftcf_gemm_f16(e->n1.p, e->lm_head, nullptr, e->logits.p, B, e->Vp, e->h, e->Vp, 0, 1, e->opt_gemm_impl == 2 ? 0 : e->opt_gemm_impl, st));
+        FTCF_TRY(ftcf_gemm_f16(e->n1.p, e->lm_head, nullptr, e->logits.p, B, e->Vp, e->h, e->Vp, 0, 1, lm_impl, st));
     } else {
         const __half* slice = e->lm_head + (size_t)e->rank * e->Vl * e->h;
-        FTCF_TRY(ftcf_gemm_f16(e->n1.p, slice, nullptr, e->logits_local.p, B, e->Vl, e->h, e->Vl, 0, 1, e->opt_gemm_impl == 2 ? 0 : e->opt_gemm_impl, st));
+        FTCF_TRY(ftcf_gemm_f16(e->n1.p, slice, nullptr, e->logits_local.p, B, e->Vl, e->h, e->Vl, 0, 1, lm_impl, st));
         FTCF_NCCL_CHECK(g_nccl.AllGather(e->logits_local.p, e->logits_gather.p, (size_t)B * e->Vl, NCCL_FLOAT32, e->comm, st));
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
         const size_t total = (size_t)e->t * B * e->Vl;

@@ -457,6 +457,16 @@ float* g_pool_part = nullptr;
 int* g_pool_tickets = nullptr;
 std::atomic<unsigned> g_pool_next{0};
 }  // namespace
+// one (partials, tickets) slot of the pool, or false when it is not reserved / too small (callers then do not split)
+bool splitk_scratch_acquire(size_t part_elems, int tickets_needed, float** part, int** tickets)
+{
+    if (g_pool_part == nullptr || part_elems > kPartElems || tickets_needed > kTicketsPerSlot) return false;
+    const unsigned slot = g_pool_next.fetch_add(1) % kPoolSlots;
+    *part = g_pool_part + (size_t)slot * kPartElems;
+    *tickets = g_pool_tickets + (size_t)slot * kTicketsPerSlot;
+    return true;
+}
+
 int skinny_reserve_scratch()
 {
     if (g_pool_part != nullptr) return FTCF_OK;

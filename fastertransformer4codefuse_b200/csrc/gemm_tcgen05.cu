@@ -17,9 +17,14 @@
 //     releases the shared-memory stage and the TMEM A-stage back to their producers.
 //   * epilogue: tcgen05.ld of the accumulator rows, per-feature dequant scale (fp32), bias, tanh-GELU, fp16/fp32 store.
 //   * fp16 weights (int8_mode = 0, LM head): same pipeline, A comes from shared memory through a UMMA descriptor.
+#include <algorithm>
+
 #include "tma_utils.cuh"
 
 namespace ftcf {
+
+bool splitk_scratch_acquire(size_t part_elems, int tickets_needed, float** part, int** tickets);   // gemm_skinny.cu
+std::atomic<int> g_tc_ksplit{1};   // tunable "tc_ksplit": k-splits for decode-size launches of the tcgen05 GEMM
 
 namespace tc {
 
@@ -111,6 +116,8 @@ struct Args {
     const __half* bias;
     void* y;
     int m, n, k, ldy, act;
+    float* part;      // split-K (gridDim.z > 1): fp32 partial sums [z][m][n]; the last CTA of a tile adds them in the order 0, 1, ...
+    int* tickets;     // one self-resetting counter per (feature tile, token tile)
 };
 
 // W8 = true : A tile = 128 rows x 128 u8  (BK = 128), converted into TMEM
@@ -134,7 +141,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * kTileM, m0 = blockIdx.y * NT;
-    const int num_kb = args.k / BK;
+    // split-K: this CTA contracts k-blocks [kb0, kb0 + num_kb) only (decode-size launches with few feature tiles: n = 5120
+    // gives 40 CTAs for 148 SMs; three k-splits stream the same weights with 120)
+    const int kb_all = args.k / BK;
+    const int kb_per = (kb_all + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int kb0 = (int)blockIdx.z * kb_per;
+    const int num_kb = max(0, min(kb_all, kb0 + kb_per) - kb0);
+    __shared__ int s_last;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -171,10 +184,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 mbar_wait(&bar_x_empty[s], ph ^ 1);
                 uint8_t* st = smem + (size_t)s * STAGE_BYTES;
                 mbar_arrive_expect_tx(&bar_full[s], STAGE_BYTES);
-                tma_load_2d(st, &map_w, &bar_full[s], kb * BK, n0);
+                tma_load_2d(st, &map_w, &bar_full[s], (kb0 + kb) * BK, n0);
 #pragma unroll
                 for (int xs = 0; xs < XSUB; ++xs)
-                    tma_load_2d(st + W_BYTES + xs * NT * 128, &map_x, &bar_full[s], kb * BK + xs * 64, m0);
+                    tma_load_2d(st + W_BYTES + xs * NT * 128, &map_x, &bar_full[s], (kb0 + kb) * BK + xs * 64, m0);
             }
         }
     } else if (warp == 1) {
@@ -211,7 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                     tc_commit(&bar_x_empty[s]);
                 }
             }
-            tc_commit(&bar_d_full);
+            tc_commit(&bar_d_full);   // (with num_kb == 0 nothing was issued: the commit completes at once)
         }
     } else {
         // ================= converter warps (u8 -> fp16 -> TMEM), then epilogue =================
@@ -259,16 +272,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             if (col_ok) sc = __half2float(args.scale[col]);
         }
         if (args.bias != nullptr && col_ok) bs = __half2float(args.bias[col]);
+        const int S = (int)gridDim.z;
+        bool finish = true;
+        if (S > 1) {
+            // publish this k-split's partial accumulators, take a ticket; only the last arriver of the tile goes on
+#pragma unroll
+            for (int c0 = 0; c0 < NT / 2; c0 += 8) {
+                uint32_t acc[8];
+                const int tcol = hf * (NT / 2) + c0;
+                tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + D_COL + tcol, acc);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int tok = m0 + tcol + j;
+                    if (col_ok && tok < args.m) args.part[((size_t)blockIdx.z * args.m + tok) * args.n + col] = num_kb > 0 ? __uint_as_float(acc[j]) : 0.f;
+                }
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight converter / epilogue warps
+            if (threadIdx.x == 64) {
+                const int tile_id = (int)blockIdx.x * (int)gridDim.y + (int)blockIdx.y;
+                const int old = atomicAdd(&args.tickets[tile_id], 1);
+                s_last = old == S - 1;
+                if (old == S - 1) args.tickets[tile_id] = 0;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            finish = s_last != 0;
+            if (finish) __threadfence();
+        }
 #pragma unroll
         for (int c0 = 0; c0 < NT / 2; c0 += 8) {
+            if (!finish) break;
             uint32_t acc[8];
             const int tcol = hf * (NT / 2) + c0;
-            tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + D_COL + tcol, acc);
+            if (S == 1) tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + D_COL + tcol, acc);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int tok = m0 + tcol + j;
                 if (!col_ok || tok >= args.m) continue;
-                float v = __uint_as_float(acc[j]);
+                float v;
+                if (S == 1) {
+                    v = __uint_as_float(acc[j]);
+                } else {
+                    v = __ldcg(&args.part[(size_t)tok * args.n + col]);
+                    for (int z = 1; z < S; ++z) v += __ldcg(&args.part[((size_t)z * args.m + tok) * args.n + col]);
+                }
                 if constexpr (EPI == EPI_W8) {
                     v = v * sc + bs;
                     if (args.act == 1) v = gelu_tanh_f32(v);
@@ -304,8 +351,17 @@ static int launch(const CUtensorMap& mw, const CUtensorMap& mx, const Args& a, c
         FTCF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const dim3 grid(ceil_div(a.n, kTileM), ceil_div(a.m, NT));
-    kern<<<grid, kThreads, smem, st>>>(mw, mx, a);
+    dim3 grid(ceil_div(a.n, kTileM), ceil_div(a.m, NT));
+    Args aa = a;
+    aa.part = nullptr;
+    aa.tickets = nullptr;
+    const int tiles = (int)(grid.x * grid.y), kb_all = a.k / BK;
+    // (measured on the 13B decode step: batch 32 12.2 -> 10.3 ms with the split, batch 16 8.1 -> 9.2 ms: only above 16 rows)
+    if (g_tc_ksplit.load(std::memory_order_relaxed) != 0 && a.m > 16 && tiles * 2 <= 148 && kb_all >= 16) {
+        int S = std::min(std::min(148 / tiles, 4), kb_all / 8);
+        if (S >= 2 && splitk_scratch_acquire((size_t)S * a.m * a.n, tiles, &aa.part, &aa.tickets)) grid.z = S;
+    }
+    kern<<<grid, kThreads, smem, st>>>(mw, mx, aa);
     FTCF_LAUNCH_CHECK();
     return FTCF_OK;
 }
@@ -374,7 +430,7 @@ int gemm_w8a16_tcgen05(const void* x, const uint8_t* w_nk, const void* scale, co
                        cudaStream_t st)
 {
     FTCF_REQUIRE(gemm_tcgen05_supported(m, n, k, 1), FTCF_ERR_UNSUPPORTED, "tcgen05 w8a16 gemm: k=%d must be a multiple of 128", k);
-    tc::Args a{static_cast<const __half*>(scale), static_cast<const __half*>(bias), y, m, n, k, n, act};
+    tc::Args a{static_cast<const __half*>(scale), static_cast<const __half*>(bias), y, m, n, k, n, act, nullptr, nullptr};
     return tc::dispatch<true, tc::EPI_W8>(x, w_nk, a, st);
 }
 
@@ -382,7 +438,7 @@ int gemm_f16_tcgen05(const void* x, const void* w_nk, const void* bias, void* y,
                      cudaStream_t st)
 {
     FTCF_REQUIRE(gemm_tcgen05_supported(m, n, k, 2), FTCF_ERR_UNSUPPORTED, "tcgen05 f16 gemm: k=%d must be a multiple of 64", k);
-    tc::Args a{nullptr, static_cast<const __half*>(bias), y, m, n, k, ldy, act};
+    tc::Args a{nullptr, static_cast<const __half*>(bias), y, m, n, k, ldy, act, nullptr, nullptr};
     if (out_f32) return tc::dispatch<false, tc::EPI_F32>(x, w_nk, a, st);
     return tc::dispatch<false, tc::EPI_F16>(x, w_nk, a, st);
 }

@@ -33,7 +33,7 @@ ids = torch.from_numpy(np.random.default_rng(1234).integers(0, cfg.vocab_size - 
 lens = torch.full((a.batch,), a.in_len, dtype=torch.int32, device=dev)
 op.forward(ids, lens, 12)          # warm-up: captures the graph
 lib = capi.load()
-CAP = 3_000_000
+CAP = 3_000_000 if a.batch <= 4 else 16_000_000
 capi.check(lib.ftcf_debug_trace_start(CAP))
 op.forward(ids, lens, 12)
 rec_t = np.dtype([("t0", "<u8"), ("t1", "<u8"), ("t2", "<u8"), ("t3", "<u8"), ("kind", "<i4"), ("cta", "<i4"), ("ncta", "<i4"),
