@@ -28,6 +28,10 @@ sys.path.insert(0, ROOT)
 
 PUBLISHED_TOKENS_PER_S = {1: 75.0, 2: 98.0}      # int8, 1xA100 / 2xA100 TP ("Tokens Per Sec")
 HBM_FALLBACK_GBS = 6650.0                        # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the decode INT8 GEMMs, from the `ncu --set full` capture in
+# profiles/r1s_gemm_skinny_ncu_full.txt: FFN1 108.55 MB, FFN2 108.77 MB, QKV 80.66 MB, O 26.26 MB -> mean of the four shapes
+# (algorithmic mean: 78.64 MB; the extra 3 % is the activations / partial sector fetches)
+GEMM_TRAFFIC_BYTES_PER_LAUNCH_TP1 = (108.55e6 + 108.77e6 + 80.66e6 + 26.26e6) / 4
 
 MODEL = dict(head_num=40, size_per_head=128, inter_size=20480, layer_num=40, vocab_size=100864, rotary_embedding_dim=128)
 B1 = dict(batch=1, in_len=1024, out_len=512)
@@ -325,7 +329,8 @@ def run_ours(args):
         "e2e": {"value": main["e2e_tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"]},
         "gpu_launches": main["launches"],
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": gemm["gbs"], "peak": peak, "unit": "GB/s", "frac": gemm["gbs"] / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": gemm["gbs"], "peak": peak, "unit": "GB/s", "frac": gemm["gbs"] / peak,
+                     "traffic": GEMM_TRAFFIC_BYTES_PER_LAUNCH_TP1 if world == 1 else None,
                      "kernel": "gemm_skinny_kernel<uint8_t,...> (weight-only INT8 GEMM, m = 1): all 160 layer GEMMs of one token",
                      "avg_launch_us": gemm["avg_launch_us"], "bytes_per_launch": gemm["bytes_per_launch"], "peak_source": peak_src},
     }

@@ -122,7 +122,7 @@ struct Args {
 
 // W8 = true : A tile = 128 rows x 128 u8  (BK = 128), converted into TMEM
 // W8 = false: A tile = 128 rows x 64 fp16 (BK = 64), consumed from shared memory
-template <bool W8, int NT, int STAGES, int EPI>
+template <bool W8, int NT, int STAGES, int EPI, bool SPLIT = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const Args args)
 {
@@ -144,9 +144,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     // split-K: this CTA contracts k-blocks [kb0, kb0 + num_kb) only (decode-size launches with few feature tiles: n = 5120
     // gives 40 CTAs for 148 SMs; three k-splits stream the same weights with 120)
     const int kb_all = args.k / BK;
-    const int kb_per = (kb_all + (int)gridDim.z - 1) / (int)gridDim.z;
-    const int kb0 = (int)blockIdx.z * kb_per;
-    const int num_kb = max(0, min(kb_all, kb0 + kb_per) - kb0);
+    const int kb_per = SPLIT ? (kb_all + (int)gridDim.z - 1) / (int)gridDim.z : kb_all;
+    const int kb0 = SPLIT ? (int)blockIdx.z * kb_per : 0;
+    const int num_kb = SPLIT ? max(0, min(kb_all, kb0 + kb_per) - kb0) : kb_all;
     __shared__ int s_last;
 
     if (threadIdx.x == 0) {
@@ -272,9 +272,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             if (col_ok) sc = __half2float(args.scale[col]);
         }
         if (args.bias != nullptr && col_ok) bs = __half2float(args.bias[col]);
-        const int S = (int)gridDim.z;
+        const int S = SPLIT ? (int)gridDim.z : 1;
         bool finish = true;
-        if (S > 1) {
+        if constexpr (SPLIT) {
             // publish this k-split's partial accumulators, take a ticket; only the last arriver of the tile goes on
 #pragma unroll
             for (int c0 = 0; c0 < NT / 2; c0 += 8) {
@@ -304,13 +304,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             if (!finish) break;
             uint32_t acc[8];
             const int tcol = hf * (NT / 2) + c0;
-            if (S == 1) tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + D_COL + tcol, acc);
+            if constexpr (!SPLIT) tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + D_COL + tcol, acc);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int tok = m0 + tcol + j;
                 if (!col_ok || tok >= args.m) continue;
                 float v;
-                if (S == 1) {
+                if constexpr (!SPLIT) {
                     v = __uint_as_float(acc[j]);
                 } else {
                     v = __ldcg(&args.part[(size_t)tok * args.n + col]);
@@ -345,10 +345,12 @@ static int launch(const CUtensorMap& mw, const CUtensorMap& mx, const Args& a, c
 {
     constexpr int BK = W8 ? 128 : 64;
     constexpr size_t smem = (size_t)STAGES * (kTileM * 128 + NT * 128 * (BK / 64)) + 1024;
-    auto kern = gemm_tc_kernel<W8, NT, STAGES, EPI>;
+    auto kern = gemm_tc_kernel<W8, NT, STAGES, EPI, false>;
+    auto kern_split = gemm_tc_kernel<W8, NT, STAGES, EPI, true>;
     static bool configured = false;
     if (!configured) {
         FTCF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FTCF_CUDA_CHECK(cudaFuncSetAttribute(kern_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid(ceil_div(a.n, kTileM), ceil_div(a.m, NT));
@@ -361,7 +363,8 @@ static int launch(const CUtensorMap& mw, const CUtensorMap& mx, const Args& a, c
         int S = std::min(std::min(148 / tiles, 4), kb_all / 8);
         if (S >= 2 && splitk_scratch_acquire((size_t)S * a.m * a.n, tiles, &aa.part, &aa.tickets)) grid.z = S;
     }
-    kern<<<grid, kThreads, smem, st>>>(mw, mx, aa);
+    if (grid.z > 1) kern_split<<<grid, kThreads, smem, st>>>(mw, mx, aa);
+    else kern<<<grid, kThreads, smem, st>>>(mw, mx, aa);
     FTCF_LAUNCH_CHECK();
     return FTCF_OK;
 }
