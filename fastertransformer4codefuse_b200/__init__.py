@@ -5,7 +5,8 @@ Layout
   csrc/binding pybind11 shims `libth_gptneox` / `libth_common` (the reference's Python surface) -> lib/
   capi.py      ctypes view of the C ABI
   gptneox_op.py, quant.py   Python mirrors of the reference operator interface over the C ABI
-  weights.py   FT-layout weight containers (synthetic init, tensor-parallel split, checkpoint files)
+  weights.py   FT-layout weight containers (synthetic init, tensor-parallel split)
+  checkpoint.py  HF -> FT checkpoint files, *.q.bin / *.s.bin, per-rank loader (the reference's converter / quant_and_save / loader)
 Nothing in this package imports `oracle/` and nothing falls back to a CPU implementation.
 """
 from .capi import FtcfError, load  # noqa: F401
