@@ -873,17 +873,15 @@ extern "C" int ftcf_mmha_decode(const ftcf_mmha_params* p, void* stream)
     cudaError_t lerr = cudaSuccess;
     // one pass where the launch is a single wave of CTAs (measured, 13B decode step: batch 8 -5 %, batch 1 equal, batch 32 +3 %)
     const bool onepass = g_mmha_onepass.load() != 0 && p->batch * p->heads <= 148 * 4;
-    const int pdl_saved = g_pdl_enabled.load();
-    if (!g_mmha_pdl.load()) g_pdl_enabled.store(0);
+    const bool pdl = g_mmha_pdl.load() != 0;
     switch (p->dh) {
-        case 64: lerr = onepass ? launch_pdl(mmha_decode_onepass_kernel<64>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp)
-                                : launch_pdl(mmha_decode_kernel<64>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
-        case 128: lerr = onepass ? launch_pdl(mmha_decode_onepass_kernel<128>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp)
-                                 : launch_pdl(mmha_decode_kernel<128>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
-        case 256: lerr = launch_pdl(mmha_decode_kernel<256>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
+        case 64: lerr = onepass ? launch_pdl_if(pdl, mmha_decode_onepass_kernel<64>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp)
+                                : launch_pdl_if(pdl, mmha_decode_kernel<64>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
+        case 128: lerr = onepass ? launch_pdl_if(pdl, mmha_decode_onepass_kernel<128>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp)
+                                 : launch_pdl_if(pdl, mmha_decode_kernel<128>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
+        case 256: lerr = launch_pdl_if(pdl, mmha_decode_kernel<256>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
         default: FTCF_REQUIRE(false, FTCF_ERR_UNSUPPORTED, "mmha: size_per_head %d (supported: 64, 128, 256)", p->dh);
     }
-    g_pdl_enabled.store(pdl_saved);
     FTCF_REQUIRE(lerr == cudaSuccess, FTCF_ERR_CUDA, "mmha launch failed: %s", cudaGetErrorString(lerr));
     FTCF_LAUNCH_CHECK();
     return FTCF_OK;

@@ -96,7 +96,7 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 // launch_pdl() calls pdl_wait() before it reads or writes anything another kernel touches.
 extern std::atomic<int> g_pdl_enabled;
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+inline cudaError_t launch_pdl_if(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
 {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
@@ -107,8 +107,13 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = g_pdl_enabled.load(std::memory_order_relaxed) ? 1 : 0;
+    cfg.numAttrs = (pdl && g_pdl_enabled.load(std::memory_order_relaxed)) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    return launch_pdl_if(true, kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -228,3 +228,55 @@ def test_pure_top_p_request(cuda):
     ids = _prompts(2, 10, cfg.vocab_size, lens, seed=3)
     _compare(op, ref, cuda, ids, lens, 12, True, top_k=[0, 3], top_p=[0.9, 0.8], temperature=[0.9, 1.0], random_seed=[21, 22],
              return_cum_log_probs=1)
+
+
+def test_full_width_properties(cuda):
+    """CodeFuse-13B layer shape (h 5120, 40 x 128 heads, inter 20480, vocab 100864; 2 layers so the oracle is not needed):
+    size-independent properties at the BASELINE width -- (a) the same request twice gives identical ids (deterministic
+    reductions, self-resetting counters), (b) graph replay == eager launches, (c) the fused residual + LayerNorm prologue
+    path and the per-operator path agree on the logits within the fp16 tolerance and on every token whose top-2 margin is
+    clear, (d) a batch of 3 ragged prompts gives each row the tokens it gets alone."""
+    cfg = W.NeoXConfig(head_num=40, size_per_head=128, inter_size=20480, layer_num=2, vocab_size=100864, rotary_embedding_dim=128,
+                       start_id=100000, end_id=100863)
+    rw = W.make_synthetic_fast(cfg, 1, 0, 1, cuda, seed=3)
+    rw.w[12 * cfg.layer_num + 3][cfg.end_id].zero_()
+    w, q, s = rw.lists()
+    op = GptNeoXOp(None, 0, cfg.head_num, cfg.size_per_head, cfg.inter_size, cfg.layer_num, cfg.vocab_size, cfg.rotary_embedding_dim,
+                   cfg.start_id, cfg.end_id, 1, 1, 1, 2048, True, w, q, s)
+    S, out = 96, 12
+    g = np.random.default_rng(2)
+    ids = torch.from_numpy(g.integers(0, cfg.vocab_size - 2, size=(3, S)).astype(np.int32)).to(cuda)
+    lens = torch.tensor([S, 40, 71], dtype=torch.int32, device=cuda)
+
+    def run(batch_rows, graph, fused, trace=False):
+        op.set_option("cuda_graph", graph)
+        op.set_option("fused_ln", fused)
+        rows = torch.tensor(batch_rows, device=cuda)
+        tr = torch.zeros(out, len(batch_rows), cfg.vocab_size, dtype=torch.float32, device=cuda) if trace else None
+        res = op.forward(ids[rows].contiguous(), lens[rows].contiguous(), out, logits_trace=tr)
+        return res[0][:, 0].cpu().numpy(), res[1].cpu().numpy(), (tr.cpu().numpy() if trace else None)
+
+    a_ids, a_len, _ = run([0], 1, 1)
+    b_ids, b_len, _ = run([0], 1, 1)
+    assert np.array_equal(a_ids, b_ids) and np.array_equal(a_len, b_len)                       # (a)
+    e_ids, _, e_log = run([0], 0, 1, trace=True)
+    assert np.array_equal(a_ids, e_ids)                                                        # (b)
+    u_ids, _, u_log = run([0], 0, 0, trace=True)
+    assert_close("fused vs per-operator logits (step 0)", e_log[0], u_log[0], LOGIT_RTOL, LOGIT_ATOL)
+    for t in range(out):                                                                       # (c)
+        top2 = np.sort(e_log[t, 0])[-2:]
+        if top2[1] - top2[0] > 4 * LOGIT_ATOL:
+            assert e_ids[0, S + t] == u_ids[0, S + t], f"step {t}"
+        elif e_ids[0, S + t] != u_ids[0, S + t]:
+            break
+    all_ids, all_len, _ = run([0, 1, 2], 1, 1)                                                 # (d)
+    for r in range(3):
+        one_ids, one_len, one_log = run([r], 0, 1, trace=True)
+        n = int(lens[r])
+        assert all_len[r, 0] == one_len[0, 0] == n + out
+        for t in range(out):
+            top2 = np.sort(one_log[t, 0])[-2:]
+            if top2[1] - top2[0] > 4 * LOGIT_ATOL:
+                assert all_ids[r, n + t] == one_ids[0, n + t], f"row {r} step {t}"
+            elif all_ids[r, n + t] != one_ids[0, n + t]:
+                break
