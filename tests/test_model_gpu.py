@@ -273,7 +273,7 @@ def test_full_width_properties(cuda):
     for r in range(3):
         one_ids, one_len, one_log = run([r], 0, 1, trace=True)
         n = int(lens[r])
-        assert all_len[r, 0] == one_len[0, 0] == n + out
+        assert all_len[r, 0] == one_len[0, 0] == S + out      # counted from max_input_length, GptNeoX.cc:687-695
         for t in range(out):
             top2 = np.sort(one_log[t, 0])[-2:]
             if top2[1] - top2[0] > 4 * LOGIT_ATOL:
