@@ -26,6 +26,7 @@ namespace ftcf {
 
 constexpr int MMHA_THREADS = 128;
 constexpr int MMHA_MAX_CHUNK = 4096;
+std::atomic<int> g_mmha_splits{0};       // tunable "mmha_splits": force the split count (0: automatic)
 std::atomic<int> g_mmha_onepass{1};      // tunable "mmha_onepass": one-pass (online softmax) decode attention; 0: the two-pass kernel
 std::atomic<int> g_prefill_mma{1};       // tunable "prefill_mma": tensor-core prefill attention (0: the CUDA-core kernel)
 std::atomic<int> g_mmha_prefetch{0};     // tunable "mmha_prefetch": L2 prefetch of the split's cache rows before the dependency wait
@@ -841,6 +842,7 @@ extern "C" int ftcf_mmha_choose_splits(int batch, int heads, int max_len)
 {
     const int ctas = batch * heads;
     int splits = ceil_div(148 * 4, ctas > 0 ? ctas : 1);
+    if (g_mmha_splits.load() > 0) splits = g_mmha_splits.load();   // experiment hook
     const int by_len = ceil_div(max_len, 128);          // at least 128 keys per split
     if (splits > by_len) splits = by_len;
     const int need = ceil_div(max_len, MMHA_MAX_CHUNK); // at most MMHA_MAX_CHUNK keys per split
@@ -872,7 +874,7 @@ extern "C" int ftcf_mmha_decode(const ftcf_mmha_params* p, void* stream)
     const dim3 grid(p->heads, p->batch, p->splits);
     cudaError_t lerr = cudaSuccess;
     // one pass where the launch is a single wave of CTAs (measured, 13B decode step: batch 8 -5 %, batch 1 equal, batch 32 +3 %)
-    const bool onepass = g_mmha_onepass.load() != 0 && p->batch * p->heads <= 148 * 4;
+    const bool onepass = g_mmha_onepass.load() == 2 || (g_mmha_onepass.load() != 0 && p->batch * p->heads <= 148 * 4);
     const bool pdl = g_mmha_pdl.load() != 0;
     switch (p->dh) {
         case 64: lerr = onepass ? launch_pdl_if(pdl, mmha_decode_onepass_kernel<64>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp)

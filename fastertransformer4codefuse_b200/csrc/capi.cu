@@ -38,7 +38,7 @@ int gemm_w8a16_tcgen05(const void* x, const uint8_t* w_nk, const void* scale, co
 int gemm_f16_tcgen05(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
                      int out_f32, cudaStream_t st);
 bool gemm_tcgen05_supported(int m, int n, int k, int elem_bytes);
-extern std::atomic<int> g_prefill_mma, g_mmha_onepass;
+extern std::atomic<int> g_prefill_mma, g_mmha_onepass, g_mmha_splits;
 extern std::atomic<int> g_mmha_pdl, g_mmha_prefetch, g_sk_carveout, g_sk_ksplit, g_sk_evict_first, g_sk_even_rows, g_tc_ksplit;
 extern std::atomic<int> g_sk_target_ctas, g_sk_prefetch_rows, g_sk_pf_ahead, g_mega_dbg, g_mega_ns, g_mega_inflight;
 
@@ -65,6 +65,7 @@ extern "C" int ftcf_set_tunable(const char* name, int value)
     else if (n == "mmha_pdl") g_mmha_pdl.store(value);
     else if (n == "prefill_mma") g_prefill_mma.store(value);
     else if (n == "mmha_onepass") g_mmha_onepass.store(value);
+    else if (n == "mmha_splits") g_mmha_splits.store(value);
     else if (n == "mmha_prefetch") g_mmha_prefetch.store(value);
     else if (n == "skinny_carveout") g_sk_carveout.store(value);
     else if (n == "mega_dbg") g_mega_dbg.store(value);

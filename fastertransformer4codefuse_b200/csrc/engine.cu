@@ -244,12 +244,31 @@ int run_layer(ftcf_gptneox* e, int l, int m, AttnFn&& attn_fn)
             FTCF_CUDA_CHECK(cudaEventRecord(e->ev_fork, st));
             FTCF_CUDA_CHECK(cudaStreamWaitEvent(sb, e->ev_fork, 0));
         }
-        FTCF_TRY(ftcf_layernorm(x, L.ln2_g, L.ln2_b, e->n2.p, m, e->h, c.layernorm_eps, sb));
-        FTCF_TRY(engine_gemm(e, sb, e->n2.p, l, 2, L.ffn1_b, e->inter.p, m, e->inter_l, e->h, 1));
+        // decode with m <= 4 rows (tensor parallel, or fused_ln = 2): the two LayerNorms run as the prologue of the GEMMs that
+        // consume them (the residual add cannot: with t > 1 its sum goes through the all-reduce first)
+        const bool ln_pro = e->opt_fused_ln != 0 && m <= 4 && e->h % 128 == 0 && e->h <= 16384 && (e->t > 1 || e->opt_fused_ln == 2);
+        auto ln_gemm = [&](cudaStream_t s2, const __half* g, const __half* b, int kind, const __half* bias, void* y, int n, int act) -> int {
+            ftcf_ln_prologue pro{};
+            pro.x = x; pro.gamma = g; pro.beta = b; pro.eps = c.layernorm_eps;
+            pro.cta_hint = fork ? e->opt_pro_ctas : 0;
+            if (c.int8_mode == 1)
+                return ftcf_gemm_w8a16_ln(&pro, static_cast<const uint8_t*>(L.w[kind]), L.scale[kind], bias, y, m, n, e->h, act, s2);
+            return ftcf_gemm_f16_ln(&pro, L.w[kind], bias, y, m, n, e->h, n, act, 0, s2);
+        };
+        if (ln_pro) {
+            FTCF_TRY(ln_gemm(sb, L.ln2_g, L.ln2_b, 2, L.ffn1_b, e->inter.p, e->inter_l, 1));
+        } else {
+            FTCF_TRY(ftcf_layernorm(x, L.ln2_g, L.ln2_b, e->n2.p, m, e->h, c.layernorm_eps, sb));
+            FTCF_TRY(engine_gemm(e, sb, e->n2.p, l, 2, L.ffn1_b, e->inter.p, m, e->inter_l, e->h, 1));
+        }
         FTCF_TRY(engine_gemm(e, sb, e->inter.p, l, 3, nullptr, e->ffn.p, m, e->h, e->inter_l, 0));
         if (fork) FTCF_CUDA_CHECK(cudaEventRecord(e->ev_join, sb));
-        FTCF_TRY(ftcf_layernorm(x, L.ln1_g, L.ln1_b, e->n1.p, m, e->h, c.layernorm_eps, st));
-        FTCF_TRY(engine_gemm(e, st, e->n1.p, l, 0, nullptr, e->qkv.p, m, 3 * e->hl, e->h, 0));
+        if (ln_pro) {
+            FTCF_TRY(ln_gemm(st, L.ln1_g, L.ln1_b, 0, nullptr, e->qkv.p, 3 * e->hl, 0));
+        } else {
+            FTCF_TRY(ftcf_layernorm(x, L.ln1_g, L.ln1_b, e->n1.p, m, e->h, c.layernorm_eps, st));
+            FTCF_TRY(engine_gemm(e, st, e->n1.p, l, 0, nullptr, e->qkv.p, m, 3 * e->hl, e->h, 0));
+        }
         FTCF_TRY(attn_fn(l));
         FTCF_TRY(engine_gemm(e, st, e->ctx.p, l, 1, nullptr, e->attn.p, m, e->h, e->hl, 0));
         if (fork) FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join, 0));
@@ -747,7 +766,7 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     FTCF_TRY(e->mmha_part.ensure((size_t)B * e->Hl * splits * (dh + 2) * 4 + 256));
     e->mega_on = e->opt_mega != 0 && e->mega_weights &&
                  mega_supported(B, e->h, e->hl, e->inter_l, dh, c.rotary_embedding_dim, c.int8_mode == 1, e->t, c.use_gptj_residual != 0);
-    e->fused_on = !e->mega_on && e->opt_fused_ln != 0 && B <= 4 && e->t == 1 && c.use_gptj_residual != 0 && e->h % 128 == 0 && e->h <= 16384;
+    e->fused_on = !e->mega_on && e->opt_fused_ln == 1 && B <= 4 && e->t == 1 && c.use_gptj_residual != 0 && e->h % 128 == 0 && e->h <= 16384;
     if (e->fused_on) {
         FTCF_TRY(e->attn_b.ensure((size_t)B * e->h * 2));
         FTCF_TRY(e->ffn_b.ensure((size_t)B * e->h * 2));

@@ -28,7 +28,7 @@ def _build(cfg, int8_mode, cuda, seed=0, mega=1, tweak=None):
     op = GptNeoXOp(None, 0, cfg.head_num, cfg.size_per_head, cfg.inter_size, cfg.layer_num, cfg.vocab_size,
                    cfg.rotary_embedding_dim, cfg.start_id, cfg.end_id, 1, 1, int8_mode, 1024, cfg.use_gptj_residual, w, q, s)
     op.set_option("mega", 1 if mega == 1 else 0)
-    op.set_option("fused_ln", 0 if mega == -1 else 1)
+    op.set_option("fused_ln", {-1: 0, -2: 2}.get(mega, 1))       # -2: LayerNorm-only prologue (the tensor-parallel decode path)
     return op, ref
 
 
@@ -75,7 +75,7 @@ def test_greedy_full_batch(cuda, int8_mode, graph, mega):
     _compare(op, ref, cuda, ids, [12, 12], 10, graph)
 
 
-@pytest.mark.parametrize("mega", [-1, 0, 1])
+@pytest.mark.parametrize("mega", [-2, -1, 0, 1])
 @pytest.mark.parametrize("int8_mode", [0, 1])
 def test_greedy_ragged_batch(cuda, int8_mode, mega):
     cfg = tiny_cfg()
@@ -280,3 +280,23 @@ def test_full_width_properties(cuda):
                 assert all_ids[r, n + t] == one_ids[0, n + t], f"row {r} step {t}"
             elif all_ids[r, n + t] != one_ids[0, n + t]:
                 break
+
+
+@pytest.mark.parametrize("layout", [1, 2])
+def test_int8_layouts_converted_at_load(cuda, layout):
+    """int8_layout 1 (plain [k,n] int8) and 2 (the reference's sm80 *.q.bin bytes) are re-laid out at engine creation and
+    give the tokens of the native B200 layout."""
+    from oracle import quant_ref as Q
+    cfg = tiny_cfg()
+    rw = W.make_synthetic(cfg, 1, 0, 1, "cpu", seed=6, keep_plain=True)
+    ref = oracle_from_rank_weights(cfg, [rw], 1)
+    w, q, s = to_cuda_lists(rw, cuda)
+    if layout == 1:
+        q_alt = [p.to(cuda) for p in rw.plain_q]
+    else:
+        q_alt = [torch.from_numpy(Q.preprocess_weights_ampere(p.numpy())).to(cuda) for p in rw.plain_q]
+    op = GptNeoXOp(None, 0, cfg.head_num, cfg.size_per_head, cfg.inter_size, cfg.layer_num, cfg.vocab_size, cfg.rotary_embedding_dim,
+                   cfg.start_id, cfg.end_id, 1, 1, 1, 1024, cfg.use_gptj_residual, w, q_alt, s, int8_layout=layout)
+    lens = [8, 5]
+    ids = _prompts(2, 8, cfg.vocab_size, lens, seed=2)
+    _compare(op, ref, cuda, ids, lens, 6, True)
