@@ -47,7 +47,7 @@ extern std::atomic<int> g_sk_target_ctas, g_sk_prefetch_rows, g_sk_pf_ahead, g_m
 using namespace ftcf;
 
 extern "C" const char* ftcf_last_error(void) { return g_err; }
-extern "C" int ftcf_abi_version(void) { return 2; }
+extern "C" int ftcf_abi_version(void) { return 3; }
 extern "C" long long ftcf_launch_count(void) { return g_launch_count.load(); }
 
 extern "C" int ftcf_set_tunable(const char* name, int value)
