@@ -485,7 +485,7 @@ __device__ __forceinline__ void stage_layernorm(const Params& p, uint8_t* opnd, 
         __half2* vh = reinterpret_cast<__half2*>(&v);
         const __half2 mean_h = sm.mean_h[b], rstd_h = sm.rstd_h[b];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) vh[j] = __hadd2_rn(__hmul2_rn(__hmul2_rn(__hsub2_rn(vh[j], mean_h), rstd_h), gh[j]), bh[j]);
+        for (int j = 0; j < 4; ++j) vh[j] = __hfma2(__hmul2_rn(__hsub2_rn(vh[j], mean_h), rstd_h), gh[j], bh[j]);
         *slot = v;
     }
     cbar();

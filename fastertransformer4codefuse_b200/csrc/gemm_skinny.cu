@@ -255,7 +255,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
                 const __half2* bh = reinterpret_cast<const __half2*>(&bq);
                 __half2* vh = reinterpret_cast<__half2*>(&v);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) vh[j] = __hadd2_rn(__hmul2_rn(__hmul2_rn(__hsub2_rn(vh[j], mean_h), rstd_h), gh[j]), bh[j]);
+                for (int j = 0; j < 4; ++j) vh[j] = __hfma2(__hmul2_rn(__hsub2_rn(vh[j], mean_h), rstd_h), gh[j], bh[j]);
                 *reinterpret_cast<uint4*>(xs + (size_t)b * pitch + vi * 8) = v;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");

@@ -2,7 +2,8 @@
 //
 // Reference behaviour restated (not ported):
 //   * LayerNorm: fp32 sum and sum-of-squares, var = E[x^2] - mean^2 + eps, then the normalisation itself in fp16:
-//     ((x - mean_h) * rstd_h) * gamma + beta with a half rounding after every operation
+//     fma((x - mean_h) * rstd_h, gamma, beta): half2 sub, mul, then ONE fused multiply-add -- what nvcc makes of the reference's
+//     hmul2(hsub2(x, mean), rstd, gamma) + beta (its SASS is HADD2, HMUL2, HFMA2; pinned on the GPU by tests/test_ref_kernels_gpu.py)
 //     (kernels/layernorm_kernels.cu:158-286, dispatched by invokeGeneralLayerNorm :1653-1735).
 //   * out = (half)(x / tp) + ffn + attn + bias with fp16 adds (kernels/add_residual_kernels.cu:116-176).
 //   * embedding row gather (kernels/gpt_kernels.cu:32-105).
@@ -77,7 +78,7 @@ layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ add1, 
             __half2* vh = reinterpret_cast<__half2*>(&v[i]);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                vh[j] = __hadd2_rn(__hmul2_rn(__hmul2_rn(__hsub2_rn(vh[j], mean_h), rstd_h), gh[j]), bh[j]);   // _rn: no mul+add contraction, every step rounds (oracle layernorm_ref)
+                vh[j] = __hfma2(__hmul2_rn(__hsub2_rn(vh[j], mean_h), rstd_h), gh[j], bh[j]);   // as the reference's object code (SASS: HADD2, HMUL2, HFMA2): the last multiply and the add are ONE fused operation
             *reinterpret_cast<uint4*>(y + row * n + vi * 8) = v[i];
         }
     }

@@ -24,13 +24,16 @@ Follows (paths relative to /root/reference/src/fastertransformer):
   * weight list order     th_op/gptneox/GptNeoXOp.h:121-174, examples/pytorch/codefuse/codefuse_example.py:182-419
   * sampling              oracle/sampling_ref.py
 
-Parity status.  The reference cannot be built or run for this path on this
-image or on sm_100, and its own tests hold no golden
-vectors for the model wiring, so this restatement is pinned only (i) for the
-quantiser by the reference's object code (oracle/_ref/libref_quant.so) and its
-KATs, and (ii) for the model wiring against HuggingFace GPTNeoXForCausalLM
-(tests/golden/, generated by tests/golden/make_golden.py).  Rounding-point
-fidelity of the fp16 kernels: PARITY UNPINNED by the reference.
+Parity status.  The reference as a whole cannot be built or run for this path on this image or on sm_100 (SURVEY.md
+section 8c), but its kernels can: oracle/Makefile compiles the reference's own .cu files (LayerNorm, residual add, decode
+attention, top-k sampling, penalties) for sm_100a into oracle/_ref/libref_kernels.so, and tests/test_ref_kernels_gpu.py
+runs them on the B200 beside our kernels AND beside this restatement.  Pinned that way: LayerNorm (bit-level: > 97 % of
+the elements identical, the rest one fp16 ulp from the fp32 reduction order), the parallel-residual add (bit-exact), the
+decode attention incl. bias + NeoX rotary + cache append (fp16 tolerance stated in the test), the sampling chain (token
+ids / finished flags / lengths identical over multi-step seeded runs).  The quantiser is pinned by the reference's
+object code on the CPU (oracle/_ref/libref_quant.so) and its KATs; the model wiring by HuggingFace GPTNeoXForCausalLM
+goldens (tests/golden/, tests/golden/make_golden.py).  Still PARITY UNPINNED by the reference: the INT8 GEMM rounding
+(its CUTLASS kernel refuses sm >= 90), the prefill attention chain's rounding points and the pure top-p walk.
 
 Tensor parallelism is emulated: `ranks` weight sets are evaluated one after the
 other and summed where the reference all-reduces.
@@ -88,8 +91,11 @@ def layernorm_ref(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     var = (x * x).sum(-1, keepdim=True) / n - mean * mean + eps
     rstd = torch.rsqrt(var)
     mean_h, rstd_h = h(mean), h(rstd)
-    v = h(h(h(x - mean_h) * rstd_h) * gamma.float())
-    return h(v + beta.float())
+    # (x - mean) and (* rstd) round to fp16 each; (* gamma + beta) is ONE fused multiply-add in the reference's object code
+    # (SASS of generalAddBiasResidualLayerNormOpt2<half2>: HADD2, HMUL2, HFMA2) -- pinned against that kernel on the GPU by
+    # tests/test_ref_kernels_gpu.py.  float64 holds the fp16 x fp16 + fp16 result exactly, so one rounding to fp16 follows.
+    t = h(h(x - mean_h) * rstd_h)
+    return (t.double() * gamma.double() + beta.double()).half().float()
 
 
 def gelu_f32(x: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,140 @@
+// TEST INFRASTRUCTURE.  C entry points over the REFERENCE's own CUDA kernels, compiled (oracle/Makefile, target
+// _ref/libref_kernels.so) from the sources where they lie under /root/reference for sm_100a:
+//   kernels/layernorm_kernels.cu                invokeGeneralLayerNorm<half>                (K4)
+//   kernels/add_residual_kernels.cu             invokeAddBiasAttentionFfnResidual<half>     (K5)
+//   kernels/decoder_masked_multihead_attention/ mmha_launch_kernel<uint16_t, 128 | 64>      (K1), parameters filled exactly as
+//                                               fusedQKV_masked_attention_dispatch does (layers/attention_layers/
+//                                               DecoderSelfAttentionLayer.cc:36-146, neox_rotary_style = true, q_scaling = 1)
+//   kernels/sampling_topk_kernels.cu            invokeCurandBatchInitialize, invokeAddBiasEndMask, invokeBatchTopKSampling (K12)
+//   kernels/sampling_topp_kernels.cu            invokeAddBiasSoftMax
+//   kernels/sampling_penalty_kernels.cu         invokeBatchApplyTemperaturePenalty, invokeBatchApplyRepetitionPenalty
+// so that `-m gpu` tests can compare our kernels with the reference's on the same inputs on the B200 (tests/test_ref_kernels_gpu.py).
+// Nothing here is part of the product; no reference source is copied.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+
+#include "src/fastertransformer/kernels/add_residual_kernels.h"
+#include "src/fastertransformer/kernels/decoder_masked_multihead_attention.h"
+#include "src/fastertransformer/kernels/layernorm_kernels.h"
+#include "src/fastertransformer/kernels/sampling_penalty_kernels.h"
+#include "src/fastertransformer/kernels/sampling_topk_kernels.h"
+#include "src/fastertransformer/kernels/sampling_topp_kernels.h"
+#include "src/fastertransformer/utils/Tensor.h"
+#include "src/fastertransformer/utils/logger.h"
+
+namespace ft = fastertransformer;
+
+// the two host symbols the kernel objects pull in (utils/logger.cc, utils/Tensor.cc are not built)
+namespace fastertransformer {
+Logger::Logger() {}
+std::string Tensor::getNumpyTypeDesc(DataType) const { return "x"; }
+}  // namespace fastertransformer
+
+// explicit instantiations live in decoder_masked_multihead_attention_{128,64}.cu
+template <typename T, int Dh, int Dh_MAX, typename KERNEL_PARAMS_TYPE>
+void mmha_launch_kernel(const KERNEL_PARAMS_TYPE& params, const cudaStream_t& stream);
+
+static cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static int done() { return cudaGetLastError() == cudaSuccess ? 0 : 1; }
+
+extern "C" int ref_layernorm_half(void* out, const void* in, const void* gamma, const void* beta, float eps, int m, int n, void* stream)
+{
+    ft::invokeGeneralLayerNorm<half>(static_cast<half*>(out), static_cast<const half*>(in), static_cast<const half*>(gamma),
+                                     static_cast<const half*>(beta), eps, m, n, (float*)nullptr, 0, S(stream));
+    return done();
+}
+
+extern "C" int ref_add_bias_attn_ffn_residual_half(void* out, const void* ffn, const void* attn, const void* x, const void* bias, int m,
+                                                   int n, int tp, void* stream)
+{
+    ft::invokeAddBiasAttentionFfnResidual<half>(static_cast<half*>(out), static_cast<const half*>(ffn), static_cast<const half*>(attn),
+                                                static_cast<const half*>(x), static_cast<const half*>(bias), m, n, tp, S(stream));
+    return done();
+}
+
+// k_cache: [B, H, Dh/8, max_len, 8] fp16, v_cache: [B, H, max_len, Dh] (the reference's layouts)
+extern "C" int ref_mmha_half(const void* qkv, const void* qkv_bias, void* k_cache, void* v_cache, void* ctx, const void* finished,
+                             const int* sequence_lengths, int batch, int heads, int dh, int rotary_dim, int memory_max_len,
+                             int max_input_len, const int* total_padding_tokens, int step, const void* masked_tokens, void* stream)
+{
+    using DataType = uint16_t;
+    Masked_multihead_attention_params<DataType> params;
+    memset(&params, 0, sizeof(params));
+    const int hidden = heads * dh;
+    if (qkv_bias != nullptr) {
+        params.q_bias = static_cast<const DataType*>(qkv_bias);
+        params.k_bias = static_cast<const DataType*>(qkv_bias) + hidden;
+        params.v_bias = static_cast<const DataType*>(qkv_bias) + 2 * hidden;
+    }
+    params.out = static_cast<DataType*>(ctx);
+    params.q = static_cast<const DataType*>(qkv);
+    params.k = static_cast<const DataType*>(qkv) + hidden;
+    params.v = static_cast<const DataType*>(qkv) + 2 * hidden;
+    params.stride = 3 * hidden;
+    params.finished = const_cast<bool*>(static_cast<const bool*>(finished));
+    params.k_cache = static_cast<DataType*>(k_cache);
+    params.v_cache = static_cast<DataType*>(v_cache);
+    params.cache_indir = nullptr;
+    params.batch_size = batch;
+    params.beam_width = 1;
+    params.memory_max_len = memory_max_len;
+    params.length_per_sample = sequence_lengths;
+    params.timestep = step - 1;
+    params.num_heads = heads;
+    params.hidden_size_per_head = dh;
+    params.rotary_embedding_dim = rotary_dim;
+    params.neox_rotary_style = true;
+    params.inv_sqrt_dh = 1.F / sqrtf((float)dh);
+    params.total_padding_tokens = total_padding_tokens;
+    params.masked_tokens = static_cast<const bool*>(masked_tokens);
+    params.max_input_length = max_input_len;
+    const cudaStream_t st = S(stream);
+    if (dh == 128) mmha_launch_kernel<DataType, 128, 128, Masked_multihead_attention_params<DataType>>(params, st);
+    else if (dh == 64) mmha_launch_kernel<DataType, 64, 64, Masked_multihead_attention_params<DataType>>(params, st);
+    else return 2;
+    return done();
+}
+
+extern "C" size_t ref_curand_state_bytes() { return sizeof(curandState_t); }
+extern "C" int ref_curand_batch_init(void* states, int batch, const unsigned long long* seeds_dev, void* stream)
+{
+    ft::invokeCurandBatchInitialize(static_cast<curandState_t*>(states), batch, seeds_dev, S(stream));
+    return done();
+}
+extern "C" int ref_temperature_penalty(float* logits, const float* temperatures, int batch, int vocab, int vocab_padded, void* stream)
+{
+    ft::invokeBatchApplyTemperaturePenalty<float>(logits, (const float*)nullptr, temperatures, batch, vocab, vocab_padded, S(stream));
+    return done();
+}
+extern "C" int ref_repetition_penalty(float* logits, const float* penalties, const int* output_ids, int batch, int vocab_padded,
+                                      const int* input_lengths, int max_input_len, int step, void* stream)
+{
+    ft::invokeBatchApplyRepetitionPenalty<float>(logits, penalties, output_ids, batch, batch, vocab_padded, input_lengths, max_input_len, step,
+                                                 ft::RepetitionPenaltyType::Multiplicative, S(stream));
+    return done();
+}
+extern "C" int ref_add_bias_end_mask(float* logits, const int* end_ids, const void* finished, int batch, int vocab, int vocab_padded, void* stream)
+{
+    ft::invokeAddBiasEndMask<float>(logits, (const float*)nullptr, end_ids, static_cast<const bool*>(finished), batch, vocab, vocab_padded, S(stream));
+    return done();
+}
+extern "C" int ref_add_bias_softmax(float* logits, const int* end_ids, const void* finished, int batch, int vocab_padded, int vocab, void* stream)
+{
+    ft::invokeAddBiasSoftMax<float>(logits, (const float*)nullptr, end_ids, static_cast<const bool*>(finished), batch, vocab_padded, vocab, S(stream));
+    return done();
+}
+// workspace == NULL: returns the size needed through *workspace_size
+extern "C" int ref_batch_topk_sampling(void* workspace, size_t* workspace_size, const float* log_probs, int* ids, int* sequence_length,
+                                       void* finished, float* cum_log_probs, void* curand_states, int max_top_k, const int* top_ks,
+                                       const float* top_ps, int vocab_padded, const int* end_ids, int batch, void* stream)
+{
+    size_t ws = *workspace_size;
+    ft::invokeBatchTopKSampling<float>(workspace, ws, log_probs, ids, sequence_length, static_cast<bool*>(finished), cum_log_probs,
+                                       (float*)nullptr, static_cast<curandState_t*>(curand_states), max_top_k, top_ks, 1.0f, top_ps,
+                                       vocab_padded, end_ids, S(stream), batch, (const bool*)nullptr);
+    *workspace_size = ws;
+    return done();
+}

@@ -25,10 +25,11 @@ then warp aggregates in order) combined with `a.u > b.u ? a : b` hands ties to
 the HIGHER thread index.  So among equal maxima the winner is the element with
 the highest (index % BLOCK_SIZE), then the lowest index.
 
-Parity status: pinned against the CPU references embedded in the reference's
-tests only indirectly (tests/unittests/test_sampling_kernels.cu checks top-k
-membership, not tie order); the tie rule above is derived from source and
-confirmed against the CUDA kernels on the GPU (tests/test_sampling_gpu.py).
+Parity status: the top-k chain is pinned against the reference's OWN kernels on
+the B200 (oracle/_ref/libref_kernels.so, tests/test_ref_kernels_gpu.py: same
+seeds, ids / finished / lengths identical over multi-step runs); the tie rule
+above is derived from source and confirmed on the GPU (tests/test_sampling_gpu.py).
+The pure top-p walk is a restatement only (unpinned).
 """
 from __future__ import annotations
 
