@@ -8,6 +8,8 @@
 //   kernels/sampling_topk_kernels.cu            invokeCurandBatchInitialize, invokeAddBiasEndMask, invokeBatchTopKSampling (K12)
 //   kernels/sampling_topp_kernels.cu            invokeAddBiasSoftMax
 //   kernels/sampling_penalty_kernels.cu         invokeBatchApplyTemperaturePenalty, invokeBatchApplyRepetitionPenalty
+//   kernels/sampling_topp_kernels.cu            invokeTopPInitialize + invokeBatchTopPSampling (pure top-p rows)
+//   kernels/stop_criteria_kernels.cu            invokeStopWordsCriterion
 // so that `-m gpu` tests can compare our kernels with the reference's on the same inputs on the B200 (tests/test_ref_kernels_gpu.py).
 // Nothing here is part of the product; no reference source is copied.
 #include <cuda_fp16.h>
@@ -22,6 +24,7 @@
 #include "src/fastertransformer/kernels/sampling_penalty_kernels.h"
 #include "src/fastertransformer/kernels/sampling_topk_kernels.h"
 #include "src/fastertransformer/kernels/sampling_topp_kernels.h"
+#include "src/fastertransformer/kernels/stop_criteria_kernels.h"
 #include "src/fastertransformer/utils/Tensor.h"
 #include "src/fastertransformer/utils/logger.h"
 
@@ -136,5 +139,44 @@ extern "C" int ref_batch_topk_sampling(void* workspace, size_t* workspace_size, 
                                        (float*)nullptr, static_cast<curandState_t*>(curand_states), max_top_k, top_ks, 1.0f, top_ps,
                                        vocab_padded, end_ids, S(stream), batch, (const bool*)nullptr);
     *workspace_size = ws;
+    return done();
+}
+
+// Pure top-p rows, as TopPSamplingLayer::runSampling drives them (layers/sampling_layers/TopPSamplingLayer.cu:256-331): `probs`
+// holds the softmax of every row (ref_add_bias_softmax).  Scratch is allocated per call (test infrastructure).
+extern "C" int ref_batch_topp_sampling(const float* probs, int* ids, int* sequence_length, void* finished, float* cum_log_probs,
+                                       void* curand_states, int batch, int vocab_padded, const int* end_ids, float max_top_p,
+                                       const float* top_ps, void* stream)
+{
+    cudaStream_t st = S(stream);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 3;
+    size_t ws = 0, cub = 0;
+    ft::invokeBatchTopPSampling<float>(nullptr, ws, cub, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                       batch, (size_t)vocab_padded, nullptr, max_top_p, top_ps, st, &prop, nullptr);
+    void* wsp = nullptr;
+    int *id_vals = nullptr, *offs = nullptr;
+    if (cudaMalloc(&wsp, ws + 256) != cudaSuccess || cudaMalloc(&id_vals, (size_t)batch * vocab_padded * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&offs, 2 * (size_t)(batch + 1) * sizeof(int)) != cudaSuccess)
+        return 4;
+    int* begin_offs = offs + (batch + 1);
+    ft::invokeTopPInitialize(id_vals, offs, begin_offs, batch, vocab_padded, st);
+    ft::invokeBatchTopPSampling<float>(wsp, ws, cub, ids, sequence_length, static_cast<bool*>(finished), cum_log_probs, nullptr, probs, id_vals,
+                                       offs, begin_offs, static_cast<curandState_t*>(curand_states), batch, (size_t)vocab_padded, end_ids,
+                                       max_top_p, top_ps, st, &prop, nullptr);
+    cudaStreamSynchronize(st);
+    cudaFree(wsp);
+    cudaFree(id_vals);
+    cudaFree(offs);
+    return done();
+}
+
+// stop_words [B, 2, n]; output_ids time-major [max_len, B]; beam_width 1 (kernels/stop_criteria_kernels.cu:24-81)
+extern "C" int ref_stop_words_criterion(const int* output_ids, const int* stop_words, void* finished, int stop_words_len, int batch, int step,
+                                        void* stream)
+{
+    ft::invokeStopWordsCriterion(output_ids, nullptr, stop_words, static_cast<bool*>(finished), 0, (size_t)stop_words_len, batch, 1, step, S(stream));
     return done();
 }

@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "gpu_next: GPU parity tests written when the round's GPU budget was spent -- not yet run on "
+                                       "hardware, NOT part of -m gpu; run them with -m gpu_next and move them to `gpu` once green")
 
 
 @pytest.fixture(scope="session")

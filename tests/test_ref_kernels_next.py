@@ -1,0 +1,127 @@
+"""NOT YET RUN ON HARDWARE (marker `gpu_next`, excluded from `-m gpu`): more parity against the reference's own kernels in
+oracle/_ref/libref_kernels.so -- pure top-p sampling (invokeTopPInitialize + invokeBatchTopPSampling, the one sampling path
+still pinned only by the CPU restatement) and the stop-word criterion.  Written after the round's GPU budget was spent; run
+with `python -m pytest tests -m gpu_next` on a B200 and promote to `gpu` when green."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fastertransformer4codefuse_b200 import capi
+from oracle import sampling_ref as S
+from helpers import stream
+
+pytestmark = [pytest.mark.gpu_next, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a B200")]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_kernels.so")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.exists(REF_SO):
+        pytest.skip(f"{REF_SO} is missing (run __graft_entry__.build() in the authoring container)")
+    lib = C.CDLL(REF_SO)
+    lib.ref_curand_state_bytes.restype = C.c_size_t
+    return lib
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+@pytest.mark.parametrize("p,want_probs", [(0.3, False), (0.9, True), (1.0, False)])
+def test_pure_top_p_vs_reference_kernels(lib, ref, cuda, p, want_probs):
+    """top_k = 0 rows: softmax -> topp_beam_topk head check -> segmented sort -> topp_sampling in the reference; our sort-free
+    bisection kernel must pick the same ids with the same seeds (a draw within fp32 rounding of a prefix sum may differ: the
+    test tolerates no mismatch on these seeds, regenerate the seeds rather than loosening it)."""
+    B, V, Vp, max_in, out_len = 3, 1000, 1008, 4, 10
+    max_len = max_in + out_len
+    end_id = V - 1
+    lens = [4, 2, 3]
+    dev = cuda
+    ids0 = np.zeros((max_len, B), dtype=np.int32)
+    ids0[:max_in] = np.random.default_rng(1).integers(0, V - 1, size=(B, max_in)).T
+    ks, ps, _ = S.setup_topk_runtime_args([0], [p], B)
+    seeds = np.asarray([11, 12, 13], np.int64)
+    t = lambda a, dt: torch.from_numpy(np.asarray(a)).to(dev, dt)
+    o_ids, o_seq = t(ids0, torch.int32), torch.full((B,), max_in - 1, dtype=torch.int32, device=dev)
+    o_fin, o_cum = torch.zeros(B, dtype=torch.uint8, device=dev), torch.zeros(B, dtype=torch.float32, device=dev)
+    d_len, d_k, d_p = t(lens, torch.int32), t(ks, torch.int32), t(ps, torch.float32)
+    d_step = torch.tensor([max_in], dtype=torch.int32, device=dev)
+    d_seeds = t(seeds.astype(np.uint64).view(np.int64), torch.int64)
+    o_states = torch.zeros(B * lib.ftcf_curand_state_bytes(), dtype=torch.uint8, device=dev)
+    capi.check(lib.ftcf_curand_init(o_states.data_ptr(), d_seeds.data_ptr(), B, stream()))
+    ws = torch.zeros(lib.ftcf_sampling_workspace_bytes(B, Vp, 1) + B * max_len * 4 + 256, dtype=torch.uint8, device=dev)
+    flag = torch.zeros(2, dtype=torch.int32, device=dev)
+    o_logits = torch.empty(B, Vp, dtype=torch.float32, device=dev)
+    sp = capi.SamplingParams(o_logits.data_ptr(), o_ids.data_ptr(), o_seq.data_ptr(), o_fin.data_ptr(), o_cum.data_ptr(), d_len.data_ptr(),
+                             d_k.data_ptr(), d_p.data_ptr(), None, None, None, None, o_states.data_ptr(), d_step.data_ptr(),
+                             flag.data_ptr(), ws.data_ptr(), B, V, Vp, 1, 0, 0, max_in, max_len, end_id, 1 if want_probs else 0, 1)
+    r_ids, r_seq = t(ids0, torch.int32), torch.full((B,), max_in - 1, dtype=torch.int32, device=dev)
+    r_fin, r_cum = torch.zeros(B, dtype=torch.bool, device=dev), torch.zeros(B, dtype=torch.float32, device=dev)
+    r_states = torch.zeros(B * ref.ref_curand_state_bytes(), dtype=torch.uint8, device=dev)
+    assert ref.ref_curand_batch_init(_p(r_states), B, _p(d_seeds), C.c_void_p(stream())) == 0
+    end_ids = torch.full((B,), end_id, dtype=torch.int32, device=dev)
+    r_logits = torch.empty(B, Vp, dtype=torch.float32, device=dev)
+    for step in range(max_in, max_len):
+        logits = np.random.default_rng(int(p * 10) * 7919 + step).normal(0, 2.0, size=(B, Vp)).astype(np.float32)
+        if step % 3 == 0:
+            logits[0, (7 * step) % (V - 1)] = 30.0             # peaked row: the head shortcut of topp_beam_topk_kernel
+        o_logits.copy_(torch.from_numpy(logits))
+        r_logits.copy_(torch.from_numpy(logits))
+        capi.check(lib.ftcf_sampling_step(sp, stream()))
+        st = C.c_void_p(stream())
+        assert ref.ref_add_bias_softmax(_p(r_logits), _p(end_ids), _p(r_fin), B, Vp, V, st) == 0
+        assert ref.ref_batch_topp_sampling(_p(r_logits), C.c_void_p(r_ids.data_ptr() + step * B * 4), _p(r_seq), _p(r_fin),
+                                           _p(r_cum) if want_probs else None, _p(r_states), B, Vp, _p(end_ids), C.c_float(float(ps.max())),
+                                           _p(d_p), st) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(o_ids[step], r_ids[step]), f"step {step}: ours {o_ids[step].tolist()} reference {r_ids[step].tolist()}"
+        assert torch.equal(o_fin.bool(), r_fin) and torch.equal(o_seq, r_seq)
+    if want_probs:
+        np.testing.assert_allclose(o_cum.cpu().numpy(), r_cum.cpu().numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_stop_words_vs_reference_kernel(lib, ref, cuda):
+    """stop_words_list [B, 2, n] (flat ids + cumulative end offsets, -1 padded) on the time-major id buffer: our step_finalize
+    kernel and invokeStopWordsCriterion must raise the same finished flags."""
+    B, V, max_in, out_len = 2, 64, 3, 8
+    max_len = max_in + out_len
+    stop = np.full((B, 2, 4), -1, dtype=np.int32)
+    stop[0, 0, :3] = [5, 6, 9]
+    stop[0, 1, :2] = [2, 3]            # phrases (5, 6) and (9)
+    stop[1, 0, :2] = [7, 7]
+    stop[1, 1, :1] = [2]               # phrase (7, 7)
+    script = {0: [1, 5, 6, 2, 2, 2, 2, 2], 1: [7, 1, 7, 7, 3, 3, 3, 3]}       # the token each row "samples" per step (greedy on a one-hot)
+    dev = cuda
+    ids0 = np.zeros((max_len, B), dtype=np.int32)
+    ids0[:max_in] = np.random.default_rng(2).integers(10, 60, size=(B, max_in)).T
+    t = lambda a, dt: torch.from_numpy(np.asarray(a)).to(dev, dt)
+    o_ids, o_seq = t(ids0, torch.int32), torch.full((B,), max_in - 1, dtype=torch.int32, device=dev)
+    o_fin, o_cum = torch.zeros(B, dtype=torch.uint8, device=dev), torch.zeros(B, dtype=torch.float32, device=dev)
+    d_len, d_k, d_p = t([3, 3], torch.int32), t([1, 1], torch.int32), t([1.0, 1.0], torch.float32)
+    d_step = torch.tensor([max_in], dtype=torch.int32, device=dev)
+    states = torch.zeros(B * lib.ftcf_curand_state_bytes(), dtype=torch.uint8, device=dev)
+    capi.check(lib.ftcf_curand_init(states.data_ptr(), t([0, 0], torch.int64).data_ptr(), B, stream()))
+    ws = torch.zeros(lib.ftcf_sampling_workspace_bytes(B, V, 1) + B * max_len * 4 + 256, dtype=torch.uint8, device=dev)
+    flag = torch.zeros(2, dtype=torch.int32, device=dev)
+    logits = torch.empty(B, V, dtype=torch.float32, device=dev)
+    d_stop = t(stop, torch.int32)
+    sp = capi.SamplingParams(logits.data_ptr(), o_ids.data_ptr(), o_seq.data_ptr(), o_fin.data_ptr(), o_cum.data_ptr(), d_len.data_ptr(),
+                             d_k.data_ptr(), d_p.data_ptr(), None, None, None, d_stop.data_ptr(), states.data_ptr(), d_step.data_ptr(),
+                             flag.data_ptr(), ws.data_ptr(), B, V, V, 1, 0, 4, max_in, max_len, V - 1, 0, 0)
+    r_fin = torch.zeros(B, dtype=torch.bool, device=dev)
+    for i, step in enumerate(range(max_in, max_len)):
+        lg = np.zeros((B, V), dtype=np.float32)
+        for b in range(B):
+            lg[b, script[b][i]] = 10.0
+        logits.copy_(torch.from_numpy(lg))
+        capi.check(lib.ftcf_sampling_step(sp, stream()))
+        torch.cuda.synchronize()
+        # the reference kernel on OUR id buffer of this step (finished rows keep their flag)
+        assert ref.ref_stop_words_criterion(_p(o_ids), _p(d_stop), _p(r_fin), 4, B, step, C.c_void_p(stream())) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(o_fin.bool(), r_fin), f"step {step}: ours {o_fin.tolist()} reference {r_fin.tolist()}"
+    assert o_fin.bool().all()
