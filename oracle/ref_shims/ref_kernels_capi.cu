@@ -10,6 +10,8 @@
 //   kernels/sampling_penalty_kernels.cu         invokeBatchApplyTemperaturePenalty, invokeBatchApplyRepetitionPenalty
 //   kernels/sampling_topp_kernels.cu            invokeTopPInitialize + invokeBatchTopPSampling (pure top-p rows)
 //   kernels/stop_criteria_kernels.cu            invokeStopWordsCriterion
+//   kernels/unfused_attention_kernels.cu        invokeAddFusedQKVBiasTranspose (prefill bias + NeoX rotary + split), invokeMaskedSoftmax
+//   kernels/decoding_kernels.cu                 invokeGatherTree (output gather with the pad gap removed)
 // so that `-m gpu` tests can compare our kernels with the reference's on the same inputs on the B200 (tests/test_ref_kernels_gpu.py).
 // Nothing here is part of the product; no reference source is copied.
 #include <cuda_fp16.h>
@@ -25,6 +27,8 @@
 #include "src/fastertransformer/kernels/sampling_topk_kernels.h"
 #include "src/fastertransformer/kernels/sampling_topp_kernels.h"
 #include "src/fastertransformer/kernels/stop_criteria_kernels.h"
+#include "src/fastertransformer/kernels/decoding_kernels.h"
+#include "src/fastertransformer/kernels/unfused_attention_kernels.h"
 #include "src/fastertransformer/utils/Tensor.h"
 #include "src/fastertransformer/utils/logger.h"
 
@@ -178,5 +182,62 @@ extern "C" int ref_stop_words_criterion(const int* output_ids, const int* stop_w
                                         void* stream)
 {
     ft::invokeStopWordsCriterion(output_ids, nullptr, stop_words, static_cast<bool*>(finished), 0, (size_t)stop_words_len, batch, 1, step, S(stream));
+    return done();
+}
+
+// Prefill: qkv [token_num, 3 * H * Dh] (padding removed) + bias -> q / k / v [B, H, S, Dh] with NeoX rotary at the token's index in
+// its own sequence, exactly as GptContextAttentionLayer drives it (layers/attention_layers/GptContextAttentionLayer.cc:140-170).
+extern "C" int ref_prefill_qkv_bias_rotary_transpose(void* q_buf, void* k_buf, void* v_buf, void* qkv, const void* qkv_bias,
+                                                     const int* padding_offset, int batch, int seq_len, int token_num, int heads, int dh,
+                                                     int rotary_dim, void* stream)
+{
+    ft::invokeAddFusedQKVBiasTranspose<half>(static_cast<half*>(q_buf), static_cast<half*>(k_buf), static_cast<half*>(v_buf),
+                                             ft::PrefixPromptBatchWeightsParam<half>{}, static_cast<half*>(qkv),
+                                             static_cast<const half*>(qkv_bias), padding_offset, batch, seq_len, token_num, heads, dh,
+                                             rotary_dim, 1, (const float*)nullptr, 0, S(stream));
+    return done();
+}
+
+// attention_score (fp16) = softmax(qk (fp32) * scale + (1 - mask) * -10000), kernels/unfused_attention_kernels.cu:255-333
+extern "C" int ref_masked_softmax_half(void* attention_score, const float* qk, const void* attention_mask, int batch, int heads, int q_len,
+                                       int k_len, float scale, void* stream)
+{
+    ft::MaskedSoftmaxParam<half, float> param;
+    param.attention_score = static_cast<half*>(attention_score);
+    param.qk = qk;
+    param.attention_mask = static_cast<const half*>(attention_mask);
+    param.batch_size = batch;
+    param.q_length = q_len;
+    param.k_length = k_len;
+    param.num_heads = heads;
+    param.qk_scale = __float2half(scale);
+    ft::invokeMaskedSoftmax(param, S(stream));
+    return done();
+}
+
+// output_ids [B, 1, max_time] <- time-major step_ids, pad gap [input_len, max_input_length) removed, as GptNeoX<T>::setOutputTensors
+// fills gatherTreeParam for sampling (models/gptneox/GptNeoX.cc:1141-1164; kernels/decoding_kernels.cu:452-580).
+// `sequence_lengths` is read and updated in place (+1, :1147-1148); `scratch` is the [B, max_time] transposed buffer.
+extern "C" int ref_gather_tree_sampling(int* output_ids, int* sequence_lengths, int* scratch, int max_time, int batch, const int* step_ids,
+                                        const int* end_tokens, const int* input_lengths, int max_input_length, void* stream)
+{
+    ft::gatherTreeParam param;
+    param.beams = scratch;
+    param.max_sequence_lengths = sequence_lengths;
+    param.max_sequence_length_final_step = 1;
+    param.max_time = max_time;
+    param.batch_size = batch;
+    param.beam_width = 1;
+    param.step_ids = step_ids;
+    param.parent_ids = nullptr;
+    param.end_tokens = end_tokens;
+    param.max_input_length = max_input_length;
+    param.prefix_soft_prompt_lengths = nullptr;
+    param.input_lengths = input_lengths;
+    param.max_prefix_soft_prompt_length = 0;
+    param.max_input_without_prompt_length = max_input_length;
+    param.stream = S(stream);
+    param.output_ids = output_ids;
+    ft::invokeGatherTree(param);
     return done();
 }
