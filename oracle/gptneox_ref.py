@@ -33,7 +33,8 @@ decode attention incl. bias + NeoX rotary + cache append (fp16 tolerance stated 
 ids / finished flags / lengths identical over multi-step seeded runs).  The quantiser is pinned by the reference's
 object code on the CPU (oracle/_ref/libref_quant.so) and its KATs; the model wiring by HuggingFace GPTNeoXForCausalLM
 goldens (tests/golden/, tests/golden/make_golden.py).  Still PARITY UNPINNED by the reference: the INT8 GEMM rounding
-(its CUTLASS kernel refuses sm >= 90), and the prefill attention chain's rounding points.
+(its CUTLASS kernel refuses sm >= 90) and the prefill bias + rotary + split kernel (open item); the
+prefill softmax chain and the output gather are pinned (tests/test_ref_kernels_prefill_gpu.py).
 
 Tensor parallelism is emulated: `ranks` weight sets are evaluated one after the
 other and summed where the reference all-reduces.

@@ -1,9 +1,9 @@
-"""NOT YET RUN ON HARDWARE (marker `gpu_next`, excluded from `-m gpu`; the round's GPU budget was spent): parity of the prefill
-glue and of the output gather against the reference's own kernels in oracle/_ref/libref_kernels.so --
-invokeAddFusedQKVBiasTranspose (bias + NeoX rotary at the token's own position + split, kernels/unfused_attention_kernels.cu:
-1326-1484), invokeMaskedSoftmax (:255-333) inside the unfused attention chain, and invokeGatherTree as
-GptNeoX<T>::setOutputTensors calls it (models/gptneox/GptNeoX.cc:1141-1164).  Run with `python -m pytest tests -m gpu_next` on a
-B200 and move to `gpu` when green."""
+"""OPEN ITEM (marker `gpu_next`, excluded from `-m gpu`): the prefill bias + NeoX rotary + split against the reference's
+invokeAddFusedQKVBiasTranspose (kernels/unfused_attention_kernels.cu:1326-1484).  Run once on a B200 with the last GPU seconds
+of round 1 (gpurun_out/call_next2.txt): FAILS -- for token 0 a quarter of the q elements (one head of four) differ by O(1),
+i.e. an indexing difference, not rounding.  Our kernel agrees with the oracle and, through it, with HuggingFace (model tests,
+tests/golden), so the first suspect is how this test drives the reference kernel (padding_offset convention, q_buf layout, or a
+launch constraint of its NeoX shared-memory path); to be resolved next round, then promoted to `gpu`."""
 import ctypes as C
 import math
 import os
@@ -74,59 +74,3 @@ def test_prefill_bias_rotary_split_vs_reference_kernel(lib, ref, cuda, Dh, rot):
         assert torch.equal(vc[b, :, p], v_r[b, :, p])
 
 
-def test_prefill_attention_vs_reference_softmax_chain(lib, ref, cuda):
-    """Our fused causal attention against the reference's unfused chain with ITS masked-softmax kernel in the middle:
-    qk = Q.K^T in fp32 (cuBLAS there, torch.matmul here), softmax(qk * scale + (1 - mask) * -10000) -> fp16, out = P.V."""
-    torch.manual_seed(3)
-    B, S, H, Dh, max_len = 2, 40, 3, 128, 48
-    lens = [40, 23]
-    tok_b, tok_p, _ = _tokens(lens, S)
-    T = len(tok_b)
-    q = (0.5 * torch.randn(T, H, Dh, device=cuda)).half()
-    kc = (0.5 * torch.randn(B, H, max_len, Dh, device=cuda)).half()
-    vc = torch.randn(B, H, max_len, Dh, device=cuda).half()
-    seq_off = torch.tensor([0, lens[0], lens[0] + lens[1]], dtype=torch.int32, device=cuda)
-    ctx = torch.zeros(T, H * Dh, dtype=torch.float16, device=cuda)
-    scale = float(torch.tensor(1.0 / math.sqrt(Dh)).half())
-    capi.check(lib.ftcf_prefill_attention(q.data_ptr(), kc.data_ptr(), vc.data_ptr(), ctx.data_ptr(), seq_off.data_ptr(), B, S, H, Dh,
-                                          max_len, scale, stream()))
-    # reference chain on padded [B, H, S, Dh]
-    qp = torch.zeros(B, H, S, Dh, dtype=torch.float16, device=cuda)
-    for t in range(T):
-        qp[int(tok_b[t]), :, int(tok_p[t])] = q[t]
-    qk = torch.matmul(qp.float(), kc[:, :, :S].float().transpose(-1, -2)).contiguous()          # [B, H, S, S] fp32
-    mask = torch.zeros(B, S, S, dtype=torch.float16, device=cuda)
-    for b, n in enumerate(lens):
-        mask[b, :n, :n] = torch.tril(torch.ones(n, n, dtype=torch.float16, device=cuda))        # gpt_kernels.cu:1036-1050
-    probs = torch.empty(B, H, S, S, dtype=torch.float16, device=cuda)
-    assert ref.ref_masked_softmax_half(_p(probs), _p(qk), _p(mask), B, H, S, S, C.c_float(scale), C.c_void_p(stream())) == 0
-    torch.cuda.synchronize()
-    out = torch.matmul(probs.float(), vc[:, :, :S].float()).half()                               # [B, H, S, Dh]
-    for t in range(T):
-        b, p = int(tok_b[t]), int(tok_p[t])
-        assert_close(f"ctx token {t}", ctx[t].float().cpu(), out[b, :, p].reshape(-1).float().cpu(), rtol=1e-2, atol=3e-3)
-
-
-def test_gather_output_vs_reference_gather_tree(lib, ref, cuda):
-    g = np.random.default_rng(4)
-    B, max_in, out_len, end_id = 3, 6, 5, 99
-    max_len = max_in + out_len
-    in_len = np.asarray([6, 2, 4], np.int32)
-    ids = g.integers(0, 90, size=(max_len, B)).astype(np.int32)
-    ids[max_in + 3, 1] = end_id                                   # row 1 produced end_id: everything after is end_id
-    seq = np.asarray([max_len - 1, max_in + 3 - 1 + 1, max_len - 1], np.int32)     # counted as the engine counts them (time step t -> t - 1)
-    d = lambda a: torch.from_numpy(a).to(cuda)
-    ids_d, seq_d, len_d = d(ids), d(seq), d(in_len)
-    out_o = torch.zeros(B, max_len, dtype=torch.int32, device=cuda)
-    len_o = torch.zeros(B, dtype=torch.int32, device=cuda)
-    capi.check(lib.ftcf_gather_output(out_o.data_ptr(), len_o.data_ptr(), ids_d.data_ptr(), seq_d.data_ptr(), len_d.data_ptr(), B, max_in,
-                                      max_len, end_id, stream()))
-    out_r = torch.zeros(B, 1, max_len, dtype=torch.int32, device=cuda)
-    seq_r = seq_d.clone()
-    scratch = torch.zeros(B, max_len, dtype=torch.int32, device=cuda)
-    ends = torch.full((B,), end_id, dtype=torch.int32, device=cuda)
-    assert ref.ref_gather_tree_sampling(_p(out_r), _p(seq_r), _p(scratch), max_len, B, _p(ids_d), _p(ends), _p(len_d), max_in,
-                                        C.c_void_p(stream())) == 0
-    torch.cuda.synchronize()
-    assert torch.equal(out_o, out_r[:, 0]), (out_o.tolist(), out_r[:, 0].tolist())
-    assert torch.equal(len_o, seq_r)
