@@ -39,6 +39,7 @@ class SamplingParams(C.Structure):
         ("batch", C.c_int32), ("vocab", C.c_int32), ("vocab_padded", C.c_int32), ("max_top_k", C.c_int32),
         ("n_last", C.c_int32), ("n_stop", C.c_int32), ("max_input_len", C.c_int32), ("max_len", C.c_int32),
         ("end_id", C.c_int32), ("want_probs", C.c_int32), ("has_top_p_rows", C.c_int32),
+        ("finished_hist_host_mapped", C.c_void_p),
     ]
 
 

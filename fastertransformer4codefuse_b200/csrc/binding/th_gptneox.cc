@@ -70,12 +70,21 @@ public:
         TORCH_CHECK(pipeline_para_size == 1, "pipeline_para_size must be 1 (codefuse_example.py:647 fixes it)");
         TORCH_CHECK((int64_t)weights_.size() == 12 * layer_num + 4, "expected ", 12 * layer_num + 4, " weight tensors, got ", weights_.size());
         const auto st = weights_[0].scalar_type();
-        TORCH_CHECK(st == at::kHalf, "only fp16 weights are implemented (the reference also takes fp32, GptNeoXOp.cc:56-105)");
+        // the reference dispatches on weights[0]: Float -> FTGptNeoX<float>, Half -> FTGptNeoX<half> (GptNeoXOp.cc:46,56-105)
+        TORCH_CHECK(st == at::kHalf || st == at::kFloat, "Wrong tensor type: weights must be fp16 or fp32");
         for (const auto& t : weights_) {                    // CHECK_INPUT, GptNeoXOp.cc:52-54
             if (t.numel() == 0) continue;
             TORCH_CHECK(t.is_cuda(), "weights must be CUDA tensors");
             TORCH_CHECK(t.is_contiguous(), "weights must be contiguous");
             TORCH_CHECK(t.scalar_type() == st, "weights must share one dtype");
+        }
+        if (st == at::kFloat) {
+            // fp32 checkpoints are accepted and rounded to fp16 once, here: the B200 engine computes in fp16 with fp32 accumulation
+            // only (a deliberate difference from FTGptNeoX<float>); the fp16 copies are what we keep alive
+            for (auto& t : weights_)
+                if (t.numel() > 0) t = t.to(at::kHalf).contiguous();
+            for (auto& t : scale_)
+                if (t.defined() && t.numel() > 0 && t.scalar_type() == at::kFloat) t = t.to(at::kHalf).contiguous();
         }
         ftcf_gptneox_config cfg{};
         cfg.head_num = (int)head_num; cfg.size_per_head = (int)size_per_head; cfg.inter_size = (int)inter_size;
@@ -123,7 +132,7 @@ public:
         void* stream = at::cuda::getCurrentCUDAStream().stream();   // captured at construction, GptNeoXOp.h:180
         check_status(ftcf_gptneox_create(&handle_, &cfg, w.data(), w.size(), n8 ? q.data() : nullptr, n8 ? s.data() : nullptr, n8, uid_ptr,
                                          stream));
-        if (const char* opts = std::getenv("FTCF_OPTIONS")) {        // experiment hook: "cuda_graph=0,mega=0"
+        if (const char* opts = std::getenv("FTCF_OPTIONS")) {        // experiment hook: "cuda_graph=0,two_branch=0"
             std::string o(opts);
             size_t p = 0;
             while (p < o.size()) {
@@ -216,6 +225,12 @@ public:
     }
 
     void set_option(const std::string& name, int64_t value) { check_status(ftcf_gptneox_set_option(handle_, name.c_str(), (int)value)); }
+    std::vector<float> last_step_ms() const      // per-step decode times of the last request (option "step_timing" = 1)
+    {
+        std::vector<float> v(8192);
+        v.resize((size_t)ftcf_gptneox_last_step_ms(handle_, v.data(), (int)v.size()));
+        return v;
+    }
     py::dict last_stats() const
     {
         py::dict d;
@@ -242,5 +257,6 @@ PYBIND11_MODULE(libth_gptneox, module)
                       int64_t, bool, std::vector<at::Tensor>, std::vector<at::Tensor>, std::vector<at::Tensor>>())
         .def("forward", &GptNeoXOp::forward)
         .def("set_option", &GptNeoXOp::set_option)
-        .def("last_stats", &GptNeoXOp::last_stats);
+        .def("last_stats", &GptNeoXOp::last_stats)
+        .def("last_step_ms", &GptNeoXOp::last_step_ms);
 }

@@ -15,6 +15,7 @@ namespace ftcf {
 static thread_local char g_err[1024] = "";
 std::atomic<long long> g_launch_count{0};
 std::atomic<int> g_pdl_enabled{1};
+std::atomic<long long> g_capture_generation{0};
 
 void set_error(const char* fmt, ...)
 {
@@ -40,7 +41,7 @@ int gemm_f16_tcgen05(const void* x, const void* w_nk, const void* bias, void* y,
 bool gemm_tcgen05_supported(int m, int n, int k, int elem_bytes);
 extern std::atomic<int> g_prefill_mma, g_mmha_onepass, g_mmha_splits;
 extern std::atomic<int> g_mmha_pdl, g_mmha_prefetch, g_sk_carveout, g_sk_ksplit, g_sk_evict_first, g_sk_even_rows, g_tc_ksplit;
-extern std::atomic<int> g_sk_target_ctas, g_sk_prefetch_rows, g_sk_pf_ahead, g_mega_dbg, g_mega_ns, g_mega_inflight;
+extern std::atomic<int> g_sk_target_ctas, g_sk_prefetch_rows, g_sk_pf_ahead;
 
 }  // namespace ftcf
 
@@ -54,6 +55,7 @@ extern "C" int ftcf_set_tunable(const char* name, int value)
 {
     FTCF_REQUIRE(name != nullptr, FTCF_ERR_INVALID, "set_tunable: null name");
     const std::string n(name);
+    g_capture_generation.fetch_add(1, std::memory_order_relaxed);   // captured launches may depend on any of these
     if (n == "pdl") g_pdl_enabled.store(value);
     else if (n == "skinny_target_ctas") { FTCF_REQUIRE(value >= 0, FTCF_ERR_INVALID, "skinny_target_ctas %d", value); g_sk_target_ctas.store(value); }
     else if (n == "skinny_ksplit") g_sk_ksplit.store(value);
@@ -68,9 +70,6 @@ extern "C" int ftcf_set_tunable(const char* name, int value)
     else if (n == "mmha_splits") g_mmha_splits.store(value);
     else if (n == "mmha_prefetch") g_mmha_prefetch.store(value);
     else if (n == "skinny_carveout") g_sk_carveout.store(value);
-    else if (n == "mega_dbg") g_mega_dbg.store(value);
-    else if (n == "mega_ns") g_mega_ns.store(value);
-    else if (n == "mega_inflight") g_mega_inflight.store(value);
     else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_tunable: unknown tunable %s", name);
     return FTCF_OK;
 }

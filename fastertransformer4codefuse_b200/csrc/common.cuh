@@ -15,6 +15,9 @@ namespace ftcf {
 // ---------------------------------------------------------------- error plumbing (host)
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launch_count;   // kernels launched by this library (bench's gpu_launches)
+// Bumped whenever an engine buffer is re-allocated or a process-wide tunable changes: a captured decode graph bakes in
+// pointers and launch shapes, so the graph cache key carries the generation it was captured under.
+extern std::atomic<long long> g_capture_generation;
 
 #define FTCF_CUDA_CHECK(expr)                                                                         \
     do {                                                                                              \

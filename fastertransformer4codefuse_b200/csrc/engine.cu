@@ -13,6 +13,7 @@
 //   * NCCL is loaded at run time (the library the process already has) and used only where the reference all-reduces.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -21,7 +22,6 @@
 #include <vector>
 
 #include "common.cuh"
-#include "decode_mega.cuh"
 
 namespace ftcf {
 int skinny_reserve_scratch();   // gemm_skinny.cu: split-K scratch must exist before the decode step is captured into a graph
@@ -126,6 +126,7 @@ struct DevBuf {
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return FTCF_OK;
+        g_capture_generation.fetch_add(1, std::memory_order_relaxed);
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -170,24 +171,35 @@ struct ftcf_gptneox {
     ncclComm_t comm = nullptr;
 
     // options
-    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_kv_prefetch = 0, opt_pro_ctas = 148, opt_mega = 0;   // mega: persistent decode-step kernel (decode_mega.cu), experimental -- measured slower than the graph (profiles/)
+    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_kv_prefetch = 0, opt_pro_ctas = 148;
 
     // request-sized buffers (grow only)
     DevBuf kv, x, x2, n1, n2, qkv, qbuf, ctx, attn, inter, ffn, logits, logits_local, logits_gather, samp_ws, small, mmha_part,
-        prompt_meta, lm_pad, layer_dev, ffn_part, att_part, gbar, attn_b, ffn_b;
+        prompt_meta, lm_pad, attn_b, ffn_b;
     bool fused_on = false;              // decode layers run with the residual + LayerNorm prologue fused into the QKV / FFN1 / LM-head GEMMs
-    mg::Params mega{};                  // persistent decode-step kernel arguments of the current request
-    bool mega_on = false, mega_weights = false;
-    const void* lm_head_tiled = nullptr;
     int32_t* host_flag = nullptr;       // mapped pinned: [0] finished count, [1] step it belongs to
     int32_t* host_flag_dev = nullptr;
     int32_t* host_stage = nullptr;      // pinned staging for small uploads / callback reads
     size_t host_stage_cap = 0;
+    int32_t* host_hist = nullptr;       // mapped pinned: [step] = 1 + finished count after that step (0: not written yet)
+    int32_t* host_hist_dev = nullptr;
+    size_t host_hist_cap = 0;           // entries
 
-    // cached decode graph
-    cudaGraphExec_t graph_exec = nullptr;
-    std::string graph_key;
-    long long graph_nodes = 0;
+    // cached decode graphs, most recently used first (alternating request shapes -- the normal serving case -- replay instead
+    // of re-capturing a 200-node graph per request)
+    struct CachedGraph {
+        std::string key;
+        cudaGraphExec_t exec = nullptr;
+        long long nodes = 0;
+    };
+    std::vector<CachedGraph> graphs;
+    static constexpr size_t kMaxGraphs = 8;
+    void drop_graphs()
+    {
+        for (auto& g : graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        graphs.clear();
+    }
 
     std::vector<float> last_step_ms;
 };
@@ -288,43 +300,6 @@ int run_layer(ftcf_gptneox* e, int l, int m, AttnFn&& attn_fn)
         FTCF_TRY(engine_allreduce(e, e->ffn.p, (size_t)m * e->h));
         FTCF_TRY(ftcf_add_bias_residual(x, e->ffn.p, e->x2.p, L.ffn2_b, m, e->h, st));
     }
-    return FTCF_OK;
-}
-
-// Tiled weight copies + per-layer pointer table of the persistent decode-step kernel (decode_mega.cuh): one contiguous bulk
-// copy per ring stage.  Built on first use (option "mega" = 1); costs a second copy of the layer weights and the LM head.
-int mega_prepare(ftcf_gptneox* e)
-{
-    if (e->mega_weights) return FTCF_OK;
-    const ftcf_gptneox_config& c = e->cfg;
-    const int L = c.layer_num;
-    if (!(e->t == 1 && c.use_gptj_residual != 0 &&
-          mega_supported(1, e->h, e->hl, e->inter_l, c.size_per_head, c.rotary_embedding_dim, c.int8_mode == 1, e->t, true)))
-        return FTCF_OK;   // not applicable: the graph of per-operator kernels runs instead
-    const int gk[4] = {e->h, e->hl, e->h, e->inter_l};
-    const int gn[4] = {3 * e->hl, e->h, e->inter_l, e->h};
-    const int wsz = c.int8_mode == 1 ? 1 : 2;
-    std::vector<mg::LayerDev> ld(L);
-    for (int l = 0; l < L; ++l) {
-        const LayerW& lw = e->layers[l];
-        for (int kind = 0; kind < 4; ++kind) {
-            ld[l].scale[kind] = lw.scale[kind];
-            e->owned.emplace_back();
-            FTCF_TRY(e->owned.back().ensure(mega_tiled_bytes(gn[kind], gk[kind] * wsz)));
-            FTCF_TRY(mega_retile(lw.w[kind], e->owned.back().p, gn[kind], gk[kind] * wsz, e->stream));
-            ld[l].w[kind] = e->owned.back().p;
-        }
-        ld[l].ln1_g = lw.ln1_g; ld[l].ln1_b = lw.ln1_b; ld[l].ln2_g = lw.ln2_g; ld[l].ln2_b = lw.ln2_b;
-        ld[l].qkv_b = lw.qkv_b; ld[l].ffn1_b = lw.ffn1_b; ld[l].res_b = lw.ffn2_b;
-    }
-    FTCF_TRY(e->layer_dev.ensure(sizeof(mg::LayerDev) * L));
-    FTCF_CUDA_CHECK(cudaMemcpyAsync(e->layer_dev.p, ld.data(), sizeof(mg::LayerDev) * L, cudaMemcpyHostToDevice, e->stream));
-    e->owned.emplace_back();
-    FTCF_TRY(e->owned.back().ensure(mega_tiled_bytes(e->Vp, e->h * 2)));
-    FTCF_TRY(mega_retile(e->lm_head, e->owned.back().p, e->Vp, e->h * 2, e->stream));
-    e->lm_head_tiled = e->owned.back().p;
-    FTCF_CUDA_CHECK(cudaStreamSynchronize(e->stream));   // ld lives on this stack frame
-    e->mega_weights = true;
     return FTCF_OK;
 }
 
@@ -453,9 +428,7 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
             e->lm_head = e->lm_pad.as<__half>();
         }
     }
-    if (status == FTCF_OK) status = e->gbar.ensure(256);
     if (status == FTCF_OK) status = skinny_reserve_scratch();
-    if (status == FTCF_OK && e->opt_mega != 0) status = mega_prepare(e);
     if (status == FTCF_OK && t > 1) {
         if (!nccl_unique_id) { set_error("create: tensor_para_size %d needs an NCCL unique id", t); status = FTCF_ERR_INVALID; }
         if (status == FTCF_OK) status = nccl_load();
@@ -485,14 +458,15 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
 extern "C" void ftcf_gptneox_destroy(ftcf_gptneox* e)
 {
     if (!e) return;
-    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    e->drop_graphs();
     for (auto& b : e->owned) b.release();
     DevBuf* bufs[] = {&e->kv, &e->x, &e->x2, &e->n1, &e->n2, &e->qkv, &e->qbuf, &e->ctx, &e->attn, &e->inter, &e->ffn, &e->logits,
-                      &e->logits_local, &e->logits_gather, &e->samp_ws, &e->small, &e->mmha_part, &e->prompt_meta, &e->lm_pad, &e->layer_dev,
-                      &e->ffn_part, &e->att_part, &e->gbar, &e->attn_b, &e->ffn_b};
+                      &e->logits_local, &e->logits_gather, &e->samp_ws, &e->small, &e->mmha_part, &e->prompt_meta, &e->lm_pad, &e->attn_b,
+                      &e->ffn_b};
     for (DevBuf* b : bufs) b->release();
     if (e->host_flag) cudaFreeHost(e->host_flag);
     if (e->host_stage) cudaFreeHost(e->host_stage);
+    if (e->host_hist) cudaFreeHost(e->host_hist);
     if (e->comm && g_nccl.ok) g_nccl.CommDestroy(e->comm);
     if (e->caller_ev) cudaEventDestroy(e->caller_ev);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -515,16 +489,8 @@ extern "C" int ftcf_gptneox_set_option(ftcf_gptneox* e, const char* name, int va
     else if (n == "fused_ln") e->opt_fused_ln = value;
     else if (n == "kv_prefetch") e->opt_kv_prefetch = value;
     else if (n == "pro_ctas") e->opt_pro_ctas = value;
-    else if (n == "mega") {
-        e->opt_mega = value;
-        if (value != 0) FTCF_TRY(mega_prepare(e));
-    }
     else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_option: unknown option %s", name);
-    if (e->graph_exec) {   // anything captured may be stale
-        cudaGraphExecDestroy(e->graph_exec);
-        e->graph_exec = nullptr;
-        e->graph_key.clear();
-    }
+    e->drop_graphs();   // anything captured may be stale
     return FTCF_OK;
 }
 
@@ -551,16 +517,6 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
     const ftcf_gptneox_config& c = e->cfg;
     cudaStream_t st = e->stream;
     const int dh = c.size_per_head;
-    if (e->mega_on) {
-        // one persistent kernel: embedding, L layers, final LayerNorm, LM head (decode_mega.cu)
-        mg::Params mp = e->mega;
-        mp.l0 = 0;
-        mp.l1 = run_layers ? c.layer_num : 0;
-        mp.embed = run_layers ? 1 : 0;
-        mp.out_ids = s.out_ids; mp.step = s.step; mp.seq_len = s.seq_len; mp.input_len = s.input_len; mp.pad_count = s.pad_count;
-        mp.finished = s.finished; mp.att_cnt = s.counters;
-        return mega_launch(mp, c.int8_mode == 1, st);
-    }
     if (e->fused_on) {
         // B <= 4, one GPU, parallel residual: the residual add of layer l-1 and the LayerNorms of layer l are the prologue of
         // layer l's QKV and FFN1 GEMMs (ftcf_gemm_*_ln); the residual stream ping-pongs between x and x2 and the branch
@@ -764,46 +720,24 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     FTCF_TRY(e->samp_ws.ensure(ws_bytes));
     const int splits = ftcf_mmha_choose_splits(B, e->Hl, max_len);
     FTCF_TRY(e->mmha_part.ensure((size_t)B * e->Hl * splits * (dh + 2) * 4 + 256));
-    e->mega_on = e->opt_mega != 0 && e->mega_weights &&
-                 mega_supported(B, e->h, e->hl, e->inter_l, dh, c.rotary_embedding_dim, c.int8_mode == 1, e->t, c.use_gptj_residual != 0);
-    e->fused_on = !e->mega_on && e->opt_fused_ln == 1 && B <= 4 && e->t == 1 && c.use_gptj_residual != 0 && e->h % 128 == 0 && e->h <= 16384;
+    e->fused_on = e->opt_fused_ln == 1 && B <= 4 && e->t == 1 && c.use_gptj_residual != 0 && e->h % 128 == 0 && e->h <= 16384;
     if (e->fused_on) {
         FTCF_TRY(e->attn_b.ensure((size_t)B * e->h * 2));
         FTCF_TRY(e->ffn_b.ensure((size_t)B * e->h * 2));
     }
-    if (e->mega_on) {
-        mg::Params& mp = e->mega;
-        mp = mg::Params{};
-        mp.layers = e->layer_dev.as<mg::LayerDev>();
-        mp.lm_rows = e->Vp;
-        mp.B = B; mp.h = e->h; mp.Hl = e->Hl; mp.hl = e->hl; mp.inter = e->inter_l; mp.dh = dh; mp.rot = c.rotary_embedding_dim;
-        mp.max_len = max_len; mp.max_in = S; mp.tp = e->t; mp.vocab = c.vocab_size;
-        mp.eps = c.layernorm_eps; mp.inv_sqrt_dh = 1.f / std::sqrt((float)dh);
-        if (mega_plan(mp, c.int8_mode == 1) != FTCF_OK) e->mega_on = false;
-    }
-    if (e->mega_on) {
-        mg::Params& mp = e->mega;
-        FTCF_TRY(e->ffn_part.ensure((size_t)mp.ks * B * e->h * 4));
-        FTCF_TRY(e->att_part.ensure((size_t)B * e->Hl * mp.att_max_units * (dh + 2) * 4 + 256));
-        mp.wte = e->wte; mp.lnf_g = e->lnf_g; mp.lnf_b = e->lnf_b; mp.lm_head = e->lm_head_tiled;
-        mp.logits = e->logits.as<float>(); mp.ld_logits = e->Vp;
-        mp.x = e->x.as<__half>(); mp.qkv = e->qkv.as<__half>(); mp.inter_buf = e->inter.as<__half>(); mp.ctx = e->ctx.as<__half>();
-        mp.ffn_part = e->ffn_part.as<float>(); mp.att_part = e->att_part.as<float>();
-        mp.kv = e->kv.as<__half>(); mp.kv_layer_elems = per_layer;
-        mp.gbar = e->gbar.as<unsigned>();
-    }
-
     // small slab layout
     Small s{};
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    // Everything a captured decode graph points into comes first and is sized by (B, max_len) only; the arrays sized by the
+    // token count T (prefill bookkeeping, never touched by the graph) come last, so two requests of the same shape with
+    // different ragged lengths see the same offsets.
     const size_t o_out_ids = carve((size_t)max_len * B * 4), o_seq = carve(B * 4), o_inlen = carve(B * 4), o_pad = carve(B * 4),
-                 o_topk = carve(B * 4), o_step = carve(4), o_cnt = carve((size_t)B * e->Hl * 4), o_tokb = carve((size_t)std::max(T, 1) * 4),
-                 o_tokp = carve((size_t)std::max(T, 1) * 4), o_seqoff = carve((B + 1) * 4), o_last = carve(B * 4),
-                 o_pids = carve((size_t)std::max(T, 1) * 4), o_gath = carve((size_t)B * max_len * 4), o_glen = carve(B * 4),
-                 o_topp = carve(B * 4), o_temp = carve(B * 4), o_rep = carve(B * 4), o_cum = carve(B * 4), o_fin = carve(B),
-                 o_seeds = carve(B * 8), o_curand = carve((size_t)B * ftcf_curand_state_bytes());
-    const bool small_grew = off > e->small.cap;
+                 o_topk = carve(B * 4), o_step = carve(4), o_cnt = carve((size_t)B * e->Hl * 4), o_seqoff = carve((B + 1) * 4),
+                 o_last = carve(B * 4), o_gath = carve((size_t)B * max_len * 4), o_glen = carve(B * 4), o_topp = carve(B * 4),
+                 o_temp = carve(B * 4), o_rep = carve(B * 4), o_cum = carve(B * 4), o_fin = carve(B), o_seeds = carve(B * 8),
+                 o_curand = carve((size_t)B * ftcf_curand_state_bytes()), o_tokb = carve((size_t)std::max(T, 1) * 4),
+                 o_tokp = carve((size_t)std::max(T, 1) * 4), o_pids = carve((size_t)std::max(T, 1) * 4);
     FTCF_TRY(e->small.ensure(off));
     char* sb = e->small.as<char>();
     s.out_ids = (int32_t*)(sb + o_out_ids); s.seq_len = (int32_t*)(sb + o_seq); s.input_len = (int32_t*)(sb + o_inlen);
@@ -813,7 +747,6 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     s.gathered = (int32_t*)(sb + o_gath); s.gathered_len = (int32_t*)(sb + o_glen); s.top_p = (float*)(sb + o_topp);
     s.temperature = (float*)(sb + o_temp); s.rep_pen = (float*)(sb + o_rep); s.cum_log = (float*)(sb + o_cum);
     s.finished = (uint8_t*)(sb + o_fin); s.seeds = (uint64_t*)(sb + o_seeds); s.curand = sb + o_curand;
-    (void)small_grew;
 
     // ---- pinned staging: [lens B][pad B][seq_len B][ks B][ps B][temps B][reps B][seeds 2B][tok_b T][tok_p T][seq_off B+1][last B][step 1]
     const size_t stage_ints = (size_t)9 * B + 2 * (size_t)std::max(T, 1) + (B + 1) + B + 1 + 2 * (size_t)B + 16;
@@ -866,6 +799,17 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     FTCF_TRY(ftcf_curand_init(s.curand, s.seeds, B, st));
     e->host_flag[0] = 0;
     e->host_flag[1] = -1;
+    if ((size_t)max_len > e->host_hist_cap) {
+        if (e->host_hist) cudaFreeHost(e->host_hist);
+        e->host_hist = nullptr;
+        e->host_hist_cap = 0;
+        const size_t want = ((size_t)max_len + 1023) & ~(size_t)1023;
+        FTCF_CUDA_CHECK(cudaHostAlloc(&e->host_hist, want * sizeof(int32_t), cudaHostAllocMapped));
+        FTCF_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->host_hist_dev), e->host_hist, 0));
+        e->host_hist_cap = want;
+        g_capture_generation.fetch_add(1, std::memory_order_relaxed);
+    }
+    memset(e->host_hist, 0, (size_t)max_len * sizeof(int32_t));   // the previous request has drained (forward ends with a sync)
 
     ftcf_sampling_params sp{};
     sp.logits = e->logits.as<float>(); sp.output_ids = s.out_ids; sp.seq_len = s.seq_len; sp.finished = s.finished;
@@ -879,6 +823,7 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     sp.batch = B; sp.vocab = c.vocab_size; sp.vocab_padded = e->Vp; sp.max_top_k = max_top_k;
     sp.max_input_len = S; sp.max_len = max_len; sp.end_id = c.end_id; sp.want_probs = r.return_cum_log_probs ? 1 : 0;
     sp.has_top_p_rows = any_topp ? 1 : 0;
+    sp.finished_hist_host_mapped = e->host_hist_dev;
 
     cudaEvent_t ev0, ev1, ev2;
     FTCF_CUDA_CHECK(cudaEventCreate(&ev0));
@@ -926,20 +871,23 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
 
     const bool want_trace = r.logits_trace != nullptr && r.logits_trace_steps > 0;
     const bool use_graph = e->opt_cuda_graph != 0 && out_len > 2 && !want_trace;
-    char keybuf[256];
-    snprintf(keybuf, sizeof(keybuf), "B%d S%d M%d k%d t%d r%d p%d l%p s%p n%d/%d kv%p x%p sm%p lg%p f%d", B, S, max_len, max_top_k, (int)any_temp,
-             (int)any_rep + 2 * (int)any_topp, sp.want_probs, (const void*)sp.optional_last_tokens, (const void*)sp.stop_words, sp.n_last, sp.n_stop, e->kv.p, e->x.p,
-             e->small.p, e->logits.p, (int)e->fused_on);
+    char keybuf[320];
+    snprintf(keybuf, sizeof(keybuf), "B%d S%d M%d k%d t%d r%d p%d l%p s%p n%d/%d kv%p x%p sm%p lg%p f%d g%lld", B, S, max_len, max_top_k,
+             (int)any_temp, (int)any_rep + 2 * (int)any_topp, sp.want_probs, (const void*)sp.optional_last_tokens, (const void*)sp.stop_words,
+             sp.n_last, sp.n_stop, e->kv.p, e->x.p, e->small.p, e->logits.p, (int)e->fused_on,
+             g_capture_generation.load(std::memory_order_relaxed));
     const std::string key(keybuf);
 
+    constexpr int kExitLag = 2;
     int steps_done = 0;
     std::vector<int32_t> last_seq(B, -1);
     std::vector<int32_t> cb_tok(B), cb_idx(B), cb_seq(B);
     for (int step = S; step < max_len; ++step) {
         const bool run_layers = !(has_prefill && step == S);
         if (use_graph && run_layers) {
-            if (!e->graph_exec || e->graph_key != key) {
-                if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+            size_t gi = 0;
+            while (gi < e->graphs.size() && e->graphs[gi].key != key) ++gi;
+            if (gi == e->graphs.size()) {
                 cudaGraph_t g = nullptr;
                 const long long n0 = g_launch_count.load();
                 FTCF_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -948,15 +896,23 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
                 cudaError_t ce = cudaStreamEndCapture(st, &g);
                 if (rc != FTCF_OK) { if (g) cudaGraphDestroy(g); return rc; }
                 FTCF_CUDA_CHECK(ce);
-                e->graph_nodes = g_launch_count.load() - n0;
-                g_launch_count.fetch_sub(e->graph_nodes);   // captured, not launched yet
-                cudaError_t ie = cudaGraphInstantiate(&e->graph_exec, g, 0);
+                ftcf_gptneox::CachedGraph cg;
+                cg.key = key;
+                cg.nodes = g_launch_count.load() - n0;
+                g_launch_count.fetch_sub(cg.nodes);   // captured, not launched yet
+                cudaError_t ie = cudaGraphInstantiate(&cg.exec, g, 0);
                 cudaGraphDestroy(g);
                 FTCF_CUDA_CHECK(ie);
-                e->graph_key = key;
+                if (e->graphs.size() >= ftcf_gptneox::kMaxGraphs) {
+                    cudaGraphExecDestroy(e->graphs.back().exec);
+                    e->graphs.pop_back();
+                }
+                e->graphs.insert(e->graphs.begin(), cg);
+            } else if (gi != 0) {
+                std::rotate(e->graphs.begin(), e->graphs.begin() + gi, e->graphs.begin() + gi + 1);
             }
-            FTCF_CUDA_CHECK(cudaGraphLaunch(e->graph_exec, st));
-            g_launch_count.fetch_add(e->graph_nodes);
+            FTCF_CUDA_CHECK(cudaGraphLaunch(e->graphs[0].exec, st));
+            g_launch_count.fetch_add(e->graphs[0].nodes);
         } else {
             FTCF_TRY(decode_step(e, s, sp, B, max_len, S, splits, run_layers));
             if (want_trace && steps_done < r.logits_trace_steps) {   // raw logits, before the sampler edits them in place
@@ -983,15 +939,23 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
             }
             if (e->rank == 0) r.callback(r.callback_user, step, cb_tok.data(), cb_idx.data(), B);
             if (e->host_flag[0] >= B) break;
-        } else if (!last_iter) {
-            // early exit without stalling the stream: look at the flag the GPU published for an EARLIER step; running a
-            // couple of extra steps after every row finished only appends end_id to rows that no longer advance.
-            const volatile int32_t* hf = e->host_flag;
-            if (hf[1] >= S && hf[0] >= B) break;
-            if (((step - S) & 7) == 7) {   // bound the run-ahead
-                FTCF_CUDA_CHECK(cudaStreamSynchronize(st));
-                if (hf[0] >= B) break;
+        } else if (!last_iter && step - kExitLag >= S) {
+            // Early exit without a per-token stream sync, and identical on every tensor-parallel rank: the decision for loop
+            // iteration `step` is taken on the finished count the sampler published FOR step - kExitLag (a step-indexed value
+            // in mapped pinned memory), which the host waits for -- it is kExitLag steps behind the launches, so the wait is
+            // normally over before it starts, and it bounds the run-ahead of the host.  Every rank therefore launches exactly
+            // (first all-finished step + kExitLag) steps and the same number of NCCL collectives.  Running kExitLag extra
+            // steps after every row finished only appends end_id to rows that no longer advance.
+            const volatile int32_t* hist = e->host_hist;
+            const int chk = step - kExitLag;
+            for (long long spin = 0; hist[chk] == 0; ++spin) {
+                if ((spin & 0xfff) == 0xfff) {
+                    const cudaError_t q = cudaStreamQuery(st);
+                    if (q == cudaSuccess) break;                  // drained: the value is there now (or the step never ran)
+                    FTCF_REQUIRE(q == cudaErrorNotReady, FTCF_ERR_CUDA, "forward: CUDA error during decode: %s", cudaGetErrorString(q));
+                }
             }
+            if (hist[chk] - 1 >= B) break;
         }
     }
     FTCF_CUDA_CHECK(cudaEventRecord(ev2, st));

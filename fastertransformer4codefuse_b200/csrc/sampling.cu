@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(1024) logits_prepare_kernel(const ftcf_samplin
         for (int i = tid; i < step; i += nt) {
             if (i >= in_len && i < p.max_input_len) continue;
             const int id = p.output_ids[(size_t)i * p.batch + b];
+            if (id < 0 || id >= Vp) continue;      // an id outside the table (the embedding lookup clamps it) penalises nothing
             const float lg = row[id];
             pl[i] = lg < 0.f ? lg * pen : lg / pen;
         }
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(1024) logits_prepare_kernel(const ftcf_samplin
         for (int i = tid; i < step; i += nt) {
             if (i >= in_len && i < p.max_input_len) continue;
             const int id = p.output_ids[(size_t)i * p.batch + b];
+            if (id < 0 || id >= Vp) continue;
             row[id] = pl[i];
         }
         __syncthreads();
@@ -419,6 +421,10 @@ __global__ void __launch_bounds__(256) step_finalize_kernel(const ftcf_sampling_
             p.finished_count_host_mapped[0] = s_cnt;
             __threadfence_system();
             p.finished_count_host_mapped[1] = step;
+        }
+        if (p.finished_hist_host_mapped != nullptr) {
+            p.finished_hist_host_mapped[step] = s_cnt + 1;
+            __threadfence_system();
         }
         *p.step = step + 1;
         trc_emit(TRC_SAMPLING, trc_t0, trc_t0, trc_t0, step, 3);   // marks the end of the step

@@ -33,11 +33,15 @@ class GptNeoXOp:
         if len(weights) != 12 * layer_num + 4:
             raise RuntimeError(f"expected {12 * layer_num + 4} weight tensors, got {len(weights)}")
         st = weights[0].dtype
-        if st != torch.float16:
-            raise RuntimeError("only fp16 weights are implemented (the reference also accepts fp32, GptNeoXOp.cc:56-105)")
+        if st not in (torch.float16, torch.float32):                 # dispatch on weights[0], GptNeoXOp.cc:46,56-105
+            raise RuntimeError("Wrong tensor type: weights must be fp16 or fp32")
         for t in weights:                                            # CHECK_INPUT, GptNeoXOp.cc:52-54
             if t.numel() and (not t.is_cuda or not t.is_contiguous() or t.dtype != st):
                 raise RuntimeError("weights must be contiguous CUDA tensors of one dtype")
+        if st == torch.float32:
+            # fp32 checkpoints are rounded to fp16 once at load: the engine computes in fp16 with fp32 accumulation only
+            weights = [t.half().contiguous() if t.numel() else t for t in weights]
+            scale = [t.half().contiguous() if t.numel() and t.dtype == torch.float32 else t for t in scale]
         self.weights, self.int8_weights, self.scale = list(weights), list(int8_weights), list(scale)   # keep alive
         self.tensor_para_size = tensor_para_size
         self.end_id = end_id
@@ -110,9 +114,9 @@ class GptNeoXOp:
         if bw != 1:
             raise RuntimeError("beam_width > 1 (beam search) is not implemented yet")
         rcl = 0 if return_cum_log_probs is None else int(return_cum_log_probs)
-        if rcl not in (0, 1, 2):
-            raise RuntimeError("return_cum_log_probs should be 0 (no return), 1 (the cumulative log probs of generated sequences) "
-                               "or 2 (the cumulative log probs of sequences)")
+        if rcl not in (0, 1):                                        # GptNeoXOp.cc:143-145
+            raise RuntimeError("return_cum_log_probs should be 0 (no return cum_log_probs), "
+                               "1 (the cumulative log probs of generated sequences)")
         B, S = input_ids.shape
         total = S + int(output_len)
         dev = input_ids.device

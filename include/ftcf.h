@@ -201,6 +201,10 @@ typedef struct {
     int32_t batch, vocab, vocab_padded, max_top_k, n_last, n_stop, max_input_len, max_len, end_id;
     int32_t want_probs;            /* 1: softmax before top-k and accumulate cum_log_probs                   */
     int32_t has_top_p_rows;        /* 1: some row has top_k == 0 (pure top-p, layers/sampling_layers/TopPSamplingLayer.cu) */
+    int32_t* finished_hist_host_mapped;  /* device-visible pinned int[max_len] (or NULL): entry [step] = 1 + #finished after
+                                            that step (0 = not written yet).  Lets the host take the early-exit decision on a
+                                            step-indexed value, i.e. identically on every tensor-parallel rank, without the
+                                            per-token stream sync of kernels/stop_criteria_kernels.cu:135-156 */
 } ftcf_sampling_params;
 size_t ftcf_sampling_workspace_bytes(int batch, int vocab_padded, int max_top_k);
 size_t ftcf_curand_state_bytes(void);

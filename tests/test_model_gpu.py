@@ -17,9 +17,9 @@ pytestmark = pytest.mark.gpu
 LOGIT_RTOL, LOGIT_ATOL = 2e-2, 3e-2
 
 
-def _build(cfg, int8_mode, cuda, seed=0, mega=1, tweak=None):
-    """mega = 1: the persistent decode-step kernel (decode_mega.cu) where it applies; 0: one kernel per operator with the
-    residual + LayerNorm prologue fused into the GEMMs (batch <= 4); -1: one kernel per operator, nothing fused."""
+def _build(cfg, int8_mode, cuda, seed=0, fused=1, tweak=None):
+    """fused = 1: the residual + LayerNorm prologue fused into the decode GEMMs (batch <= 4, the default); 0: one kernel per
+    operator, nothing fused; 2: LayerNorm-only prologue (the tensor-parallel decode path)."""
     rw = W.make_synthetic(cfg, 1, 0, int8_mode, "cpu", seed=seed, keep_plain=True)
     if tweak is not None:
         tweak(rw)
@@ -27,8 +27,7 @@ def _build(cfg, int8_mode, cuda, seed=0, mega=1, tweak=None):
     w, q, s = to_cuda_lists(rw, cuda)
     op = GptNeoXOp(None, 0, cfg.head_num, cfg.size_per_head, cfg.inter_size, cfg.layer_num, cfg.vocab_size,
                    cfg.rotary_embedding_dim, cfg.start_id, cfg.end_id, 1, 1, int8_mode, 1024, cfg.use_gptj_residual, w, q, s)
-    op.set_option("mega", 1 if mega == 1 else 0)
-    op.set_option("fused_ln", {-1: 0, -2: 2}.get(mega, 1))       # -2: LayerNorm-only prologue (the tensor-parallel decode path)
+    op.set_option("fused_ln", fused)
     return op, ref
 
 
@@ -65,21 +64,21 @@ def _compare(op, ref, cuda, ids, lens, out_len, graph, **kw):
     return res, exp
 
 
-@pytest.mark.parametrize("mega", [-1, 0, 1])
+@pytest.mark.parametrize("fused", [0, 1])
 @pytest.mark.parametrize("int8_mode", [0, 1])
 @pytest.mark.parametrize("graph", [False, True])
-def test_greedy_full_batch(cuda, int8_mode, graph, mega):
+def test_greedy_full_batch(cuda, int8_mode, graph, fused):
     cfg = tiny_cfg()
-    op, ref = _build(cfg, int8_mode, cuda, mega=mega)
+    op, ref = _build(cfg, int8_mode, cuda, fused=fused)
     ids = _prompts(2, 12, cfg.vocab_size, [12, 12])
     _compare(op, ref, cuda, ids, [12, 12], 10, graph)
 
 
-@pytest.mark.parametrize("mega", [-2, -1, 0, 1])
+@pytest.mark.parametrize("fused", [0, 1, 2])
 @pytest.mark.parametrize("int8_mode", [0, 1])
-def test_greedy_ragged_batch(cuda, int8_mode, mega):
+def test_greedy_ragged_batch(cuda, int8_mode, fused):
     cfg = tiny_cfg()
-    op, ref = _build(cfg, int8_mode, cuda, seed=3, mega=mega)
+    op, ref = _build(cfg, int8_mode, cuda, seed=3, fused=fused)
     lens = [16, 5, 11, 1]
     ids = _prompts(4, 16, cfg.vocab_size, lens, seed=7)
     _compare(op, ref, cuda, ids, lens, 8, False)
@@ -94,53 +93,48 @@ def test_sequential_residual(cuda):
     _compare(op, ref, cuda, ids, lens, 6, False)
 
 
-@pytest.mark.parametrize("mega", [-1, 0, 1])
-def test_dh128_full_rotary(cuda, mega):
+@pytest.mark.parametrize("fused", [0, 1])
+def test_dh128_full_rotary(cuda, fused):
     cfg = tiny_cfg(head_num=2, size_per_head=128, rotary_embedding_dim=128, inter_size=1024, layer_num=3)
-    op, ref = _build(cfg, 1, cuda, seed=11, mega=mega)
+    op, ref = _build(cfg, 1, cuda, seed=11, fused=fused)
     lens = [20, 13]
     ids = _prompts(2, 20, cfg.vocab_size, lens, seed=2)
     _compare(op, ref, cuda, ids, lens, 12, False)
     _compare(op, ref, cuda, ids, lens, 12, True)
 
 
-@pytest.mark.parametrize("mega", [-1, 0, 1])
-def test_seeded_topk_sampling_and_cum_log_probs(cuda, mega):
+@pytest.mark.parametrize("fused", [0, 1])
+def test_seeded_topk_sampling_and_cum_log_probs(cuda, fused):
     cfg = tiny_cfg()
-    op, ref = _build(cfg, 1, cuda, seed=1, mega=mega)
+    op, ref = _build(cfg, 1, cuda, seed=1, fused=fused)
     lens = [10, 7, 10]
     ids = _prompts(3, 10, cfg.vocab_size, lens, seed=4)
     _compare(op, ref, cuda, ids, lens, 8, False, top_k=[8, 8, 8], top_p=[0.9, 0.9, 0.9], temperature=[0.7, 0.7, 0.7],
              repetition_penalty=[1.1, 1.1, 1.1], random_seed=[42, 42, 43], return_cum_log_probs=1)
 
 
-@pytest.mark.parametrize("mega", [-1, 0, 1])
-def test_single_token_prompt_runs_decoder_only(cuda, mega):
+@pytest.mark.parametrize("fused", [0, 1])
+def test_single_token_prompt_runs_decoder_only(cuda, fused):
     cfg = tiny_cfg()
-    op, ref = _build(cfg, 1, cuda, seed=2, mega=mega)
+    op, ref = _build(cfg, 1, cuda, seed=2, fused=fused)
     ids = _prompts(2, 1, cfg.vocab_size, [1, 1], seed=3)
     _compare(op, ref, cuda, ids, [1, 1], 6, False)
 
 
 @pytest.mark.parametrize("int8_mode", [0, 1])
-def test_mega_long_context_batch8(cuda, int8_mode):
-    """The persistent decode kernel with several attention work units per head (context > 160 keys), KV tiles that straddle
-    the pad gap of ragged prompts, 8 sequences (all 8 MMA columns live), k extents of 3 and 12 k-steps and a head count that
-    does not divide the CTA count."""
+def test_long_context_batch8(cuda, int8_mode):
+    """Context > 160 keys (several split-KV units per head), KV tiles that straddle the pad gap of ragged prompts, 8 sequences,
+    k extents of 3 and 12 k-steps and a head count that does not divide the CTA count."""
     cfg = tiny_cfg(head_num=6, size_per_head=64, inter_size=1536, layer_num=2, vocab_size=640, rotary_embedding_dim=16, end_id=639)
-    op, ref = _build(cfg, int8_mode, cuda, seed=21, mega=1)
+    op, ref = _build(cfg, int8_mode, cuda, seed=21)
     lens = [230, 1, 97, 230, 161, 64, 200, 33]
     ids = _prompts(8, 230, cfg.vocab_size, lens, seed=5)
     _compare(op, ref, cuda, ids, lens, 5, False)
-    res_g, _ = _compare(op, ref, cuda, ids, lens, 5, True)
-    # the per-operator path must agree with the persistent kernel on every id
-    op.set_option("mega", 0)
-    res_k = op.forward(torch.from_numpy(ids).to(cuda), torch.tensor(lens, dtype=torch.int32, device=cuda), 5)
-    assert torch.equal(res_g[0], res_k[0])
+    _compare(op, ref, cuda, ids, lens, 5, True)
 
 
-@pytest.mark.parametrize("mega", [-1, 0, 1])
-def test_finished_rows_stop_advancing(cuda, mega):
+@pytest.mark.parametrize("fused", [0, 1])
+def test_finished_rows_stop_advancing(cuda, fused):
     """Rows that sample end_id stop (their attention work disappears from the schedule, the sampler pins them to end_id)
     while the others go on; the request ends early once every row is finished.  The end_id row of the LM head is scaled up
     so that end_id wins within a few steps for some rows."""
@@ -149,7 +143,7 @@ def test_finished_rows_stop_advancing(cuda, mega):
     def tweak(rw):
         rw.w[12 * cfg.layer_num + 3][cfg.end_id] *= 6.0
 
-    op, ref = _build(cfg, 1, cuda, seed=6, mega=mega, tweak=tweak)
+    op, ref = _build(cfg, 1, cuda, seed=6, fused=fused, tweak=tweak)
     lens = [6, 6, 3, 5]
     ids = _prompts(4, 6, cfg.vocab_size, lens, seed=8)
     res, exp = _compare(op, ref, cuda, ids, lens, 16, False, top_k=[6, 6, 6, 6], top_p=[1.0] * 4, random_seed=[1, 2, 3, 4])
@@ -223,7 +217,7 @@ def test_pybind_shim_runs_the_reference_call(cuda):
 def test_pure_top_p_request(cuda):
     """top_k = 0 with top_p > 0 through the whole engine (graph replay), mixed with a top-k row."""
     cfg = tiny_cfg()
-    op, ref = _build(cfg, 1, cuda, seed=8, mega=0)
+    op, ref = _build(cfg, 1, cuda, seed=8, fused=0)
     lens = [10, 6]
     ids = _prompts(2, 10, cfg.vocab_size, lens, seed=3)
     _compare(op, ref, cuda, ids, lens, 12, True, top_k=[0, 3], top_p=[0.9, 0.8], temperature=[0.9, 1.0], random_seed=[21, 22],

@@ -1,7 +1,7 @@
-"""GPU parity of the prefill attention and of the output gather against the reference's own kernels in
-oracle/_ref/libref_kernels.so: invokeMaskedSoftmax (kernels/unfused_attention_kernels.cu:255-333) inside the unfused attention
-chain, and invokeGatherTree as GptNeoX<T>::setOutputTensors calls it (models/gptneox/GptNeoX.cc:1141-1164).  (Both ran green on
-a B200 with the last GPU seconds of round 1, gpurun_out/call_next2.txt, and were promoted from `gpu_next`.)"""
+"""GPU parity of the prefill path against the reference's own kernels in oracle/_ref/libref_kernels.so: the bias + NeoX rotary +
+split (invokeAddFusedQKVBiasTranspose, kernels/unfused_attention_kernels.cu:1326-1484), invokeMaskedSoftmax
+(kernels/unfused_attention_kernels.cu:255-333) inside the unfused attention chain, and invokeGatherTree as
+GptNeoX<T>::setOutputTensors calls it (models/gptneox/GptNeoX.cc:1141-1164)."""
 import ctypes as C
 import math
 import os
@@ -39,6 +39,46 @@ def _tokens(lens, S):
             pad_off.append(skipped)
         skipped += S - n
     return np.asarray(tok_b, np.int32), np.asarray(tok_p, np.int32), np.asarray(pad_off, np.int32)
+
+
+@pytest.mark.parametrize("Dh,rot", [(64, 16), (128, 128), (128, 32)])
+@pytest.mark.parametrize("B,S,H,lens", [(2, 12, 4, [12, 7]), (3, 40, 5, [1, 40, 23])])
+def test_prefill_bias_rotary_split_vs_reference_kernel(lib, ref, cuda, Dh, rot, B, S, H, lens):
+    """K7.  (Round 1 parked this comparison as failing: the harness passed `.data_ptr()` of temporaries, the caching allocator
+    handed tok_b's block to tok_p, and our kernel then scattered K/V rows with batch = position, out of bounds.  Every device
+    tensor is held in a named variable now.)"""
+    torch.manual_seed(Dh + rot + S)
+    max_len = S + 8
+    tok_b, tok_p, pad_off = _tokens(lens, S)
+    T = len(tok_b)
+    qkv = torch.randn(T, 3 * H * Dh, device=cuda).half()
+    bias = (0.1 * torch.randn(3 * H * Dh, device=cuda)).half()
+    tok_b_d, tok_p_d, pad_off_d = (torch.from_numpy(a).to(cuda) for a in (tok_b, tok_p, pad_off))
+    # ours
+    q_o = torch.zeros(T, H, Dh, dtype=torch.float16, device=cuda)
+    kc = torch.zeros(B, H, max_len, Dh, dtype=torch.float16, device=cuda)
+    vc = torch.zeros_like(kc)
+    capi.check(lib.ftcf_prefill_qkv_rotary_scatter(qkv.data_ptr(), bias.data_ptr(), q_o.data_ptr(), kc.data_ptr(), vc.data_ptr(),
+                                                   tok_b_d.data_ptr(), tok_p_d.data_ptr(), T, H, Dh, rot, max_len, stream()))
+    # the reference's kernel: q / k / v [B, H, S, Dh]; it also rewrites its qkv input in place, hence the clone
+    q_r = torch.zeros(B, H, S, Dh, dtype=torch.float16, device=cuda)
+    k_r, v_r = torch.zeros_like(q_r), torch.zeros_like(q_r)
+    qkv_in = qkv.clone()
+    assert ref.ref_prefill_qkv_bias_rotary_transpose(_p(q_r), _p(k_r), _p(v_r), _p(qkv_in), _p(bias), _p(pad_off_d), B, S, T, H, Dh, rot,
+                                                     C.c_void_p(stream())) == 0
+    torch.cuda.synchronize()
+    q_o_c, kc_c, vc_c, q_r_c, k_r_c, v_r_c = (x.float().cpu() for x in (q_o, kc, vc, q_r, k_r, v_r))
+    for t in range(T):
+        b, p = int(tok_b[t]), int(tok_p[t])
+        # rotary in fp32 on fp16 inputs, rounded once: identical up to the sincos implementation (one fp16 ulp)
+        assert_close(f"q token {t}", q_o_c[t], q_r_c[b, :, p], rtol=2e-3, atol=1e-3)
+        assert_close(f"k token {t}", kc_c[b, :, p], k_r_c[b, :, p], rtol=2e-3, atol=1e-3)
+        assert torch.equal(vc_c[b, :, p], v_r_c[b, :, p])
+        # the non-rotary dims are bias adds only: bit-exact
+        assert torch.equal(q_o_c[t][:, rot:], q_r_c[b, :, p][:, rot:])
+    # nothing outside the prompts was written (pad gap and the decode part of the cache stay untouched)
+    for b, n in enumerate(lens):
+        assert not kc_c[b, :, n:].any() and not vc_c[b, :, n:].any()
 
 
 def test_prefill_attention_vs_reference_softmax_chain(lib, ref, cuda):

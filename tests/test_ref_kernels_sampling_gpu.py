@@ -104,7 +104,8 @@ def test_stop_words_vs_reference_kernel(lib, ref, cuda):
     d_len, d_k, d_p = t([3, 3], torch.int32), t([1, 1], torch.int32), t([1.0, 1.0], torch.float32)
     d_step = torch.tensor([max_in], dtype=torch.int32, device=dev)
     states = torch.zeros(B * lib.ftcf_curand_state_bytes(), dtype=torch.uint8, device=dev)
-    capi.check(lib.ftcf_curand_init(states.data_ptr(), t([0, 0], torch.int64).data_ptr(), B, stream()))
+    d_seeds = t([0, 0], torch.int64)           # held: a temporary's block could be handed to the next allocation
+    capi.check(lib.ftcf_curand_init(states.data_ptr(), d_seeds.data_ptr(), B, stream()))
     ws = torch.zeros(lib.ftcf_sampling_workspace_bytes(B, V, 1) + B * max_len * 4 + 256, dtype=torch.uint8, device=dev)
     flag = torch.zeros(2, dtype=torch.int32, device=dev)
     logits = torch.empty(B, V, dtype=torch.float32, device=dev)
