@@ -47,9 +47,15 @@ class PrefetchHint(C.Structure):
     _fields_ = [("w", C.c_void_p), ("n", C.c_int32), ("row_bytes", C.c_int32)]
 
 
+class TpExchange(C.Structure):
+    _fields_ = [("peer_data", C.c_void_p * 8), ("peer_counter", C.c_void_p * 8), ("tp", C.c_int32), ("rank", C.c_int32),
+                ("m_max", C.c_int32), ("h", C.c_int32), ("step", C.c_void_p), ("step_base", C.c_int32), ("layer_num", C.c_int32)]
+
+
 class LnPrologue(C.Structure):
     _fields_ = [("x", C.c_void_p), ("add_ffn", C.c_void_p), ("add_attn", C.c_void_p), ("add_bias", C.c_void_p),
-                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("x_out", C.c_void_p), ("eps", C.c_float), ("cta_hint", C.c_int32)]
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("x_out", C.c_void_p), ("eps", C.c_float), ("cta_hint", C.c_int32),
+                ("tp_exchange", C.POINTER(TpExchange)), ("tp_layer", C.c_int32)]
 
 
 class GptNeoXConfig(C.Structure):
@@ -111,6 +117,9 @@ SIGNATURES = {
                                      C.c_int, C.c_void_p]),
     "ftcf_gemm_f16_ln": (C.c_int, [C.POINTER(LnPrologue), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_void_p]),
+    "ftcf_gemm_w8a16_tp_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TpExchange), C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_void_p]),
+    "ftcf_tp_gather_residual": (C.c_int, [C.POINTER(TpExchange), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ftcf_transpose_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ftcf_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "ftcf_add_bias_residual_layernorm": (C.c_int, [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),

@@ -39,6 +39,11 @@ int gemm_w8a16_tcgen05(const void* x, const uint8_t* w_nk, const void* scale, co
 int gemm_f16_tcgen05(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
                      int out_f32, cudaStream_t st);
 bool gemm_tcgen05_supported(int m, int n, int k, int elem_bytes);
+int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n, int k, int act,
+                      const SkPro* pro, cudaStream_t st, const ftcf_tp_exchange* push = nullptr, int push_kind = 0, int push_layer = 0);
+bool gemm_decode_supported(int m, int n, int k);
+extern std::atomic<int> g_dg_target_ctas, g_dg_min_kb, g_dg_evict_first;
+std::atomic<int> g_decode_impl{3};   // tunable "decode_impl": 3 = tcgen05 decode GEMM for int8 at m <= 32 (default), 1 = round-1 streaming mma.sync kernel
 extern std::atomic<int> g_prefill_mma, g_mmha_onepass, g_mmha_splits;
 extern std::atomic<int> g_mmha_pdl, g_mmha_prefetch, g_sk_carveout, g_sk_ksplit, g_sk_evict_first, g_sk_even_rows, g_tc_ksplit;
 extern std::atomic<int> g_sk_target_ctas, g_sk_prefetch_rows, g_sk_pf_ahead;
@@ -70,6 +75,10 @@ extern "C" int ftcf_set_tunable(const char* name, int value)
     else if (n == "mmha_splits") g_mmha_splits.store(value);
     else if (n == "mmha_prefetch") g_mmha_prefetch.store(value);
     else if (n == "skinny_carveout") g_sk_carveout.store(value);
+    else if (n == "decode_target_ctas") g_dg_target_ctas.store(value);
+    else if (n == "decode_min_kb") g_dg_min_kb.store(value);
+    else if (n == "decode_evict_first") g_dg_evict_first.store(value);
+    else if (n == "decode_impl") g_decode_impl.store(value);
     else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_tunable: unknown tunable %s", name);
     return FTCF_OK;
 }
@@ -77,6 +86,7 @@ extern "C" int ftcf_set_tunable(const char* name, int value)
 // ---------------------------------------------------------------- per-CTA timeline (debug)
 namespace ftcf {
 int trace_install_gemm_skinny(TraceRec*, unsigned*, unsigned);
+int trace_install_gemm_decode(TraceRec*, unsigned*, unsigned);
 int trace_install_attention(TraceRec*, unsigned*, unsigned);
 int trace_install_norm_residual(TraceRec*, unsigned*, unsigned);
 int trace_install_sampling(TraceRec*, unsigned*, unsigned);
@@ -87,6 +97,7 @@ static unsigned g_trace_cap = 0;
 static int trace_install_all(TraceRec* buf, unsigned* cnt, unsigned cap)
 {
     int rc = trace_install_gemm_skinny(buf, cnt, cap);
+    if (rc == FTCF_OK) rc = trace_install_gemm_decode(buf, cnt, cap);
     if (rc == FTCF_OK) rc = trace_install_attention(buf, cnt, cap);
     if (rc == FTCF_OK) rc = trace_install_norm_residual(buf, cnt, cap);
     if (rc == FTCF_OK) rc = trace_install_sampling(buf, cnt, cap);
@@ -136,9 +147,10 @@ extern "C" int ftcf_device_check(void)
     return FTCF_OK;
 }
 
-// m at or below which the streaming (skinny) kernel is used in auto mode; above it the tcgen05 kernel takes over
-// when the shape is one it supports.
-static constexpr int kSkinnyMaxM = 11;   // measured (decode step, 13B int8): batch 8 skinny 5.4 vs tcgen05 6.9 ms; batch 16: 8.7 vs 8.1; batch 32: 15.1 vs 12.3
+// Auto mode (impl 0) for the INT8 GEMM: m <= 32 rows -> the tcgen05 decode kernel (gemm_decode.cu), more rows -> the tcgen05
+// prefill kernel (gemm_tcgen05.cu).  impl 1 forces round 1's streaming mma.sync kernel (kept for A/B measurements and for
+// k that is not a multiple of 128), impl 2 the prefill kernel, impl 3 the decode kernel.
+static constexpr int kSkinnyMaxM = 11;   // fp16 weights only: above it the tcgen05 kernel takes over
 
 extern "C" int ftcf_gemm_w8a16_ex(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n,
                                   int k, int act, int impl, const ftcf_prefetch_hint* next, void* stream)
@@ -148,6 +160,9 @@ extern "C" int ftcf_gemm_w8a16_ex(const void* x, const uint8_t* w_nk, const void
     cudaStream_t st = as_stream(stream);
     if (impl == 1) return gemm_w8a16_skinny(x, w_nk, scale, bias, y, m, n, k, act, next, st);
     if (impl == 2) return gemm_w8a16_tcgen05(x, w_nk, scale, bias, y, m, n, k, act, st);
+    if (impl == 3) return gemm_w8a16_decode(x, w_nk, scale, bias, y, m, n, k, act, nullptr, st);
+    if (g_decode_impl.load(std::memory_order_relaxed) == 3 && gemm_decode_supported(m, n, k))
+        return gemm_w8a16_decode(x, w_nk, scale, bias, y, m, n, k, act, nullptr, st);
     if (m > kSkinnyMaxM && gemm_tcgen05_supported(m, n, k, 1)) return gemm_w8a16_tcgen05(x, w_nk, scale, bias, y, m, n, k, act, st);
     return gemm_w8a16_skinny(x, w_nk, scale, bias, y, m, n, k, act, next, st);
 }
@@ -164,7 +179,31 @@ extern "C" int ftcf_gemm_w8a16_ln(const ftcf_ln_prologue* pro, const uint8_t* w_
     FTCF_REQUIRE(pro && w_nk && scale && y, FTCF_ERR_INVALID, "gemm_w8a16_ln: null operand");
     FTCF_REQUIRE(act == 0 || act == 1, FTCF_ERR_INVALID, "gemm_w8a16_ln: act %d", act);
     FTCF_REQUIRE(pro->x_out == nullptr || pro->x_out != pro->x, FTCF_ERR_INVALID, "gemm_w8a16_ln: x_out must not alias x");
+    if (g_decode_impl.load(std::memory_order_relaxed) == 3 && m <= 4 && gemm_decode_supported(m, n, k)) {
+        SkPro sp{};
+        sp.x = static_cast<const __half*>(pro->x); sp.add_ffn = static_cast<const __half*>(pro->add_ffn);
+        sp.add_attn = static_cast<const __half*>(pro->add_attn); sp.add_bias = static_cast<const __half*>(pro->add_bias);
+        sp.gamma = static_cast<const __half*>(pro->gamma); sp.beta = static_cast<const __half*>(pro->beta);
+        sp.x_out = static_cast<__half*>(pro->x_out); sp.eps = pro->eps; sp.cta_hint = pro->cta_hint;
+        if (pro->tp_exchange != nullptr && pro->tp_exchange->tp > 1) {
+            const ftcf_tp_exchange& ex = *pro->tp_exchange;
+            FTCF_REQUIRE(ex.tp <= 8 && ex.rank >= 0 && ex.rank < ex.tp && m <= ex.m_max && k == ex.h && ex.step != nullptr, FTCF_ERR_INVALID,
+                         "gemm_w8a16_ln: bad tensor-parallel gather (tp %d rank %d m %d/%d k %d/%d)", ex.tp, ex.rank, m, ex.m_max, k, ex.h);
+            sp.tpx = ex;
+            sp.tp_layer = pro->tp_layer;
+        }
+        return gemm_w8a16_decode(nullptr, w_nk, scale, bias, y, m, n, k, act, &sp, as_stream(stream));
+    }
+    FTCF_REQUIRE(pro->tp_exchange == nullptr, FTCF_ERR_UNSUPPORTED, "gemm_w8a16_ln: the tensor-parallel gather needs the tcgen05 decode kernel "
+                 "(m <= 4, k a multiple of 128)");
     return gemm_w8a16_skinny_ln(*pro, w_nk, scale, bias, y, m, n, k, act, as_stream(stream));
+}
+
+extern "C" int ftcf_gemm_w8a16_tp_push(const void* x, const uint8_t* w_nk, const void* scale, const ftcf_tp_exchange* ex, int kind, int layer,
+                                       int m, int n, int k, void* stream)
+{
+    FTCF_REQUIRE(x && w_nk && scale && ex, FTCF_ERR_INVALID, "gemm_w8a16_tp_push: null operand");
+    return gemm_w8a16_decode(x, w_nk, scale, nullptr, nullptr, m, n, k, 0, nullptr, as_stream(stream), ex, kind, layer);
 }
 
 extern "C" int ftcf_gemm_f16_ln(const ftcf_ln_prologue* pro, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy,

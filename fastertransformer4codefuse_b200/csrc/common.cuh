@@ -120,6 +120,22 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Fused prologue of the decode layer (m <= 4 tokens): the CTA builds its own copy of the GEMM input in shared memory,
+//   r = ((add_ffn + add_attn) + add_bias) + x       (the PREVIOUS layer's parallel-residual add, add_residual_kernels.cu:116-176;
+//                                                    skipped when add_ffn == NULL)
+//   a = LayerNorm(r; gamma, beta)                   (layernorm_kernels.cu:158-286: fp32 statistics, half2 normalisation)
+// instead of reading what a residual kernel and a LayerNorm kernel wrote: two launches (and their kernel boundaries, ~5 us of
+// idle HBM each) leave the critical path of every layer.  Every CTA recomputes the same 10 KB row (L2 hits); CTA 0 stores r.
+struct SkPro {
+    const __half *x, *add_ffn, *add_attn, *add_bias, *gamma, *beta;
+    __half* x_out;
+    float eps;
+    int cta_hint;
+    ftcf_tp_exchange tpx;   // tpx.tp > 1: the partials of exchange `tp_layer` stand in for add_ffn / add_attn (tensor-parallel gather)
+    int tp_layer;
+};
+
+
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -177,6 +193,27 @@ __device__ __forceinline__ uint4 ld_stream_16(const void* p)
 // 128-bit cached read-only load (activations re-read by many warps).
 __device__ __forceinline__ uint4 ld_ro_16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
+// four biased bytes (value q + 128) -> (b0-128, b1-128) and (b2-128, b3-128) as half2 bit patterns: PRMT builds 0x64xx
+// (= 1024 + b, exact in fp16), one HSUB2 subtracts 1152 -- the same constant trick as the reference's
+// interleaved_numeric_conversion.h:69-75, without its interleaved byte order
+__device__ __forceinline__ void u8x4_to_h2x2(uint32_t w, uint32_t& lo, uint32_t& hi)
+{
+    lo = __byte_perm(w, 0x64646464u, 0x4140);
+    hi = __byte_perm(w, 0x64646464u, 0x4342);
+    const uint32_t magic = 0x64806480u;   // 1152.0 = 1024 + 128, twice
+    asm("sub.f16x2 %0, %1, %2;" : "=r"(lo) : "r"(lo), "r"(magic));
+    asm("sub.f16x2 %0, %1, %2;" : "=r"(hi) : "r"(hi), "r"(magic));
+}
+// mma.sync m16n8k16, fp16 operands, fp32 accumulate (the legacy tensor path: streaming fp16 GEMM and prefill attention)
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1)
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 __device__ __forceinline__ float2 h2_to_f2(uint32_t u)
 {
     return __half22float2(*reinterpret_cast<const __half2*>(&u));
@@ -185,6 +222,82 @@ __device__ __forceinline__ uint32_t f2_to_h2(float a, float b)
 {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------- tensor-parallel exchange (ftcf_tp_exchange, include/ftcf.h)
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_sys_add_u32(unsigned* p, unsigned v)
+{
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+struct TpIndex {
+    int slot;
+    unsigned uses;
+};
+__device__ __forceinline__ TpIndex tp_index(const ftcf_tp_exchange& ex, int layer)
+{
+    const int g = (*ex.step - ex.step_base) * ex.layer_num + layer;
+    return {g & 1, (unsigned)(g >> 1) + 1u};
+}
+__device__ __forceinline__ size_t tp_data_offset(const ftcf_tp_exchange& ex, int slot, int kind, int src)
+{
+    return ((size_t)(slot * 2 + kind) * ex.tp + src) * ex.m_max * ex.h;      // in fp16 elements
+}
+__device__ __forceinline__ int tp_counter_index(int slot, int kind) { return (slot * 2 + kind) * 32; }   // uint32 units, 128 bytes apart
+// Gather side, one thread: block until both kinds of this rank's (slot) counters show `uses` complete exchanges.  Bounded: a
+// peer that died traps this kernel instead of hanging the GPU for good.
+__device__ __forceinline__ void tp_wait_counters(const ftcf_tp_exchange& ex, const TpIndex ix)
+{
+    const unsigned want = ix.uses * (unsigned)ex.tp * (unsigned)((ex.h + 127) / 128);
+    const unsigned* c = ex.peer_counter[ex.rank];
+    for (int kind = 0; kind < 2; ++kind) {
+        const unsigned* p = c + tp_counter_index(ix.slot, kind);
+        for (long long spin = 0; ld_acquire_sys_u32(p) < want; ++spin)
+            if (spin > (1ll << 28)) __trap();
+    }
+}
+// 8 consecutive elements of row b of the all-reduced residual:  sum_r [((ffn_r + attn_r) + bias) + half(x / tp)]  in fp32, rounded
+// once.  Same fp16 adds per rank as residual_kernel<0> (kernels/add_residual_kernels.cu:116-176).
+__device__ __forceinline__ uint4 tp_gather_vec(const ftcf_tp_exchange& ex, int slot, int b, int vi, uint4 xv, const __half* bias)
+{
+    const __half* data = static_cast<const __half*>(ex.peer_data[ex.rank]);
+    const float inv_tp = 1.f / ex.tp;
+    __half2 xs[4];
+    const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+    uint4 bv = make_uint4(0, 0, 0, 0);
+    if (bias != nullptr) bv = *reinterpret_cast<const uint4*>(bias + vi * 8);
+    const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(xh[j]);
+        xs[j] = __floats2half2_rn(f.x * inv_tp, f.y * inv_tp);
+    }
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < ex.tp; ++r) {
+        const uint4 fv = __ldcg(reinterpret_cast<const uint4*>(data + tp_data_offset(ex, slot, 1, r) + (size_t)b * ex.h + vi * 8));
+        const uint4 av = __ldcg(reinterpret_cast<const uint4*>(data + tp_data_offset(ex, slot, 0, r) + (size_t)b * ex.h + vi * 8));
+        const __half2* fh = reinterpret_cast<const __half2*>(&fv);
+        const __half2* ah = reinterpret_cast<const __half2*>(&av);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __half2 o = __hadd2(fh[j], ah[j]);
+            if (bias != nullptr) o = __hadd2(o, bh[j]);
+            o = __hadd2(o, xs[j]);
+            const float2 f = __half22float2(o);
+            acc[2 * j] += f.x;
+            acc[2 * j + 1] += f.y;
+        }
+    }
+    uint4 out;
+    __half2* oh = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+    return out;
 }
 
 // tanh-form GELU in fp32: x * 0.5 * (1 + tanh(0.79788456 * (x + 0.044715 x^3))).  tanh through exp so that the

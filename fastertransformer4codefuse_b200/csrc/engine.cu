@@ -24,7 +24,8 @@
 #include "common.cuh"
 
 namespace ftcf {
-int skinny_reserve_scratch();   // gemm_skinny.cu: split-K scratch must exist before the decode step is captured into a graph
+int splitk_reserve_for_stream(cudaStream_t st);   // gemm_decode.cu: split-K scratch must exist before the decode step is captured
+void splitk_release_for_stream(cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------ NCCL (dlopen)
 typedef struct ncclComm* ncclComm_t;
@@ -169,9 +170,17 @@ struct ftcf_gptneox {
     const __half *wte = nullptr, *lnf_g = nullptr, *lnf_b = nullptr, *lm_head = nullptr;
     std::vector<DevBuf> owned;   // re-laid-out weights (fp16 transposes, plain->B200 int8)
     ncclComm_t comm = nullptr;
+    // tensor-parallel exchange area (ftcf_tp_exchange): decode-size all-reduces run as remote stores from the O / FFN2 GEMM
+    // epilogues into every rank's area (CUDA IPC over NVLink) instead of residual kernel + ncclAllReduce
+    void* tp_area = nullptr;            // this rank's [data][counters], cudaMalloc'ed (IPC-exportable)
+    size_t tp_data_bytes = 0;
+    std::vector<void*> tp_opened;       // peers' areas mapped into this process
+    ftcf_tp_exchange tpx{};             // peer pointers + geometry; step / step_base are filled per request
+    bool tp_fused = false;              // the exchange area is up on EVERY rank
+    static constexpr int kTpMaxRows = 32;
 
     // options
-    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_kv_prefetch = 0, opt_pro_ctas = 148;
+    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_kv_prefetch = 0, opt_pro_ctas = 148, opt_tp_fused = 1;
 
     // request-sized buffers (grow only)
     DevBuf kv, x, x2, n1, n2, qkv, qbuf, ctx, attn, inter, ffn, logits, logits_local, logits_gather, samp_ws, small, mmha_part,
@@ -231,6 +240,64 @@ int engine_allreduce(ftcf_gptneox* e, void* buf, size_t count)
     return FTCF_OK;
 }
 
+// Sets up the tensor-parallel exchange area: every rank exports its area as a CUDA IPC handle, the handles travel through
+// ncclAllGather, every rank maps its peers.  All ranks then agree (ncclAllReduce MIN) on whether everybody succeeded; if not,
+// the engine keeps the residual kernel + ncclAllReduce path (never a CPU path) -- e.g. when peer access is not available.
+int tp_exchange_setup(ftcf_gptneox* e)
+{
+    const int t = e->t;
+    if (t <= 1 || t > 8 || e->cfg.int8_mode != 1 || e->h % 128 != 0) return FTCF_OK;
+    cudaStream_t st = e->stream;
+    e->tp_data_bytes = (size_t)2 * 2 * t * ftcf_gptneox::kTpMaxRows * e->h * sizeof(__half);
+    const size_t area_bytes = e->tp_data_bytes + 4 * 128;
+    int ok = 1;
+    cudaIpcMemHandle_t mine{};
+    if (cudaMalloc(&e->tp_area, area_bytes) != cudaSuccess || cudaMemset(e->tp_area, 0, area_bytes) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine, e->tp_area) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    char* dev_handles = nullptr;
+    FTCF_CUDA_CHECK(cudaMalloc(&dev_handles, (size_t)t * 64 + 16));
+    FTCF_CUDA_CHECK(cudaMemcpyAsync(dev_handles + (size_t)e->rank * 64, &mine, 64, cudaMemcpyHostToDevice, st));
+    FTCF_NCCL_CHECK(g_nccl.AllGather(dev_handles + (size_t)e->rank * 64, dev_handles, 64, /*ncclChar*/ 0, e->comm, st));
+    std::vector<cudaIpcMemHandle_t> all(t);
+    FTCF_CUDA_CHECK(cudaMemcpyAsync(all.data(), dev_handles, (size_t)t * 64, cudaMemcpyDeviceToHost, st));
+    FTCF_CUDA_CHECK(cudaStreamSynchronize(st));
+    std::vector<void*> base(t, nullptr);
+    for (int r = 0; r < t && ok; ++r) {
+        if (r == e->rank) { base[r] = e->tp_area; continue; }
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+            break;
+        }
+        e->tp_opened.push_back(p);
+        base[r] = p;
+    }
+    // unanimous?
+    int32_t* flag = reinterpret_cast<int32_t*>(dev_handles + (size_t)t * 64);
+    int32_t okv = ok;
+    FTCF_CUDA_CHECK(cudaMemcpyAsync(flag, &okv, 4, cudaMemcpyHostToDevice, st));
+    FTCF_NCCL_CHECK(g_nccl.AllReduce(flag, flag, 1, /*ncclInt32*/ 2, /*ncclMin*/ 3, e->comm, st));
+    FTCF_CUDA_CHECK(cudaMemcpyAsync(&okv, flag, 4, cudaMemcpyDeviceToHost, st));
+    FTCF_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(dev_handles);
+    e->tp_fused = okv == 1;
+    if (e->tp_fused) {
+        ftcf_tp_exchange& x = e->tpx;
+        x = ftcf_tp_exchange{};
+        for (int r = 0; r < t; ++r) {
+            x.peer_data[r] = base[r];
+            x.peer_counter[r] = reinterpret_cast<uint32_t*>(static_cast<char*>(base[r]) + e->tp_data_bytes);
+        }
+        x.tp = t; x.rank = e->rank; x.m_max = ftcf_gptneox::kTpMaxRows; x.h = e->h; x.layer_num = e->cfg.layer_num;
+    }
+    return FTCF_OK;
+}
+
 #define FTCF_TRY(expr)                \
     do {                              \
         int _s = (expr);              \
@@ -239,7 +306,7 @@ int engine_allreduce(ftcf_gptneox* e, void* buf, size_t count)
 
 // One transformer layer on m rows of x (in place: x <- layer(x)).  attn_fn fills e->ctx from e->qkv.
 template <typename AttnFn>
-int run_layer(ftcf_gptneox* e, int l, int m, AttnFn&& attn_fn)
+int run_layer(ftcf_gptneox* e, int l, int m, AttnFn&& attn_fn, bool tp_decode = false)
 {
     const LayerW& L = e->layers[l];
     const ftcf_gptneox_config& c = e->cfg;
@@ -273,7 +340,11 @@ int run_layer(ftcf_gptneox* e, int l, int m, AttnFn&& attn_fn)
             FTCF_TRY(ftcf_layernorm(x, L.ln2_g, L.ln2_b, e->n2.p, m, e->h, c.layernorm_eps, sb));
             FTCF_TRY(engine_gemm(e, sb, e->n2.p, l, 2, L.ffn1_b, e->inter.p, m, e->inter_l, e->h, 1));
         }
-        FTCF_TRY(engine_gemm(e, sb, e->inter.p, l, 3, nullptr, e->ffn.p, m, e->h, e->inter_l, 0));
+        // decode rows with the exchange area up: the O / FFN2 epilogues store their tiles into every rank's area and
+        // ftcf_tp_gather_residual rebuilds the all-reduced residual (no residual kernel, no ncclAllReduce)
+        const bool tp_push = tp_decode && e->tp_fused && e->opt_tp_fused != 0 && c.int8_mode == 1 && m <= ftcf_gptneox::kTpMaxRows;
+        if (tp_push) FTCF_TRY(ftcf_gemm_w8a16_tp_push(e->inter.p, static_cast<const uint8_t*>(L.w[3]), L.scale[3], &e->tpx, 1, l, m, e->h, e->inter_l, sb));
+        else FTCF_TRY(engine_gemm(e, sb, e->inter.p, l, 3, nullptr, e->ffn.p, m, e->h, e->inter_l, 0));
         if (fork) FTCF_CUDA_CHECK(cudaEventRecord(e->ev_join, sb));
         if (ln_pro) {
             FTCF_TRY(ln_gemm(st, L.ln1_g, L.ln1_b, 0, nullptr, e->qkv.p, 3 * e->hl, 0));
@@ -282,11 +353,16 @@ int run_layer(ftcf_gptneox* e, int l, int m, AttnFn&& attn_fn)
             FTCF_TRY(engine_gemm(e, st, e->n1.p, l, 0, nullptr, e->qkv.p, m, 3 * e->hl, e->h, 0));
         }
         FTCF_TRY(attn_fn(l));
-        FTCF_TRY(engine_gemm(e, st, e->ctx.p, l, 1, nullptr, e->attn.p, m, e->h, e->hl, 0));
+        if (tp_push) FTCF_TRY(ftcf_gemm_w8a16_tp_push(e->ctx.p, static_cast<const uint8_t*>(L.w[1]), L.scale[1], &e->tpx, 0, l, m, e->h, e->hl, st));
+        else FTCF_TRY(engine_gemm(e, st, e->ctx.p, l, 1, nullptr, e->attn.p, m, e->h, e->hl, 0));
         if (fork) FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join, 0));
         // ffn2_b slot holds the summed (o + ffn2) bias, already divided by t (huggingface_convert.py:35-41,192-206)
-        FTCF_TRY(ftcf_add_bias_attn_ffn_residual(x, e->ffn.p, e->attn.p, x, L.ffn2_b, m, e->h, e->t, st));
-        FTCF_TRY(engine_allreduce(e, x, (size_t)m * e->h));
+        if (tp_push) {
+            FTCF_TRY(ftcf_tp_gather_residual(&e->tpx, l, x, L.ffn2_b, x, m, st));
+        } else {
+            FTCF_TRY(ftcf_add_bias_attn_ffn_residual(x, e->ffn.p, e->attn.p, x, L.ffn2_b, m, e->h, e->t, st));
+            FTCF_TRY(engine_allreduce(e, x, (size_t)m * e->h));
+        }
     } else {
         FTCF_TRY(ftcf_layernorm(x, L.ln1_g, L.ln1_b, e->n1.p, m, e->h, c.layernorm_eps, st));
         FTCF_TRY(engine_gemm(e, st, e->n1.p, l, 0, nullptr, e->qkv.p, m, 3 * e->hl, e->h, 0));
@@ -428,7 +504,8 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
             e->lm_head = e->lm_pad.as<__half>();
         }
     }
-    if (status == FTCF_OK) status = skinny_reserve_scratch();
+    if (status == FTCF_OK) status = splitk_reserve_for_stream(e->stream);
+    if (status == FTCF_OK) status = splitk_reserve_for_stream(e->side);
     if (status == FTCF_OK && t > 1) {
         if (!nccl_unique_id) { set_error("create: tensor_para_size %d needs an NCCL unique id", t); status = FTCF_ERR_INVALID; }
         if (status == FTCF_OK) status = nccl_load();
@@ -439,6 +516,7 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
             if (r != 0) { set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); status = FTCF_ERR_NCCL; }
         }
     }
+    if (status == FTCF_OK && t > 1) status = tp_exchange_setup(e);
     if (status == FTCF_OK) {
         if (cudaHostAlloc(&e->host_flag, 64, cudaHostAllocMapped) != cudaSuccess ||
             cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->host_flag_dev), e->host_flag, 0) != cudaSuccess) {
@@ -467,14 +545,16 @@ extern "C" void ftcf_gptneox_destroy(ftcf_gptneox* e)
     if (e->host_flag) cudaFreeHost(e->host_flag);
     if (e->host_stage) cudaFreeHost(e->host_stage);
     if (e->host_hist) cudaFreeHost(e->host_hist);
+    for (void* p : e->tp_opened) cudaIpcCloseMemHandle(p);
+    if (e->tp_area) cudaFree(e->tp_area);
     if (e->comm && g_nccl.ok) g_nccl.CommDestroy(e->comm);
     if (e->caller_ev) cudaEventDestroy(e->caller_ev);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->ev_join2) cudaEventDestroy(e->ev_join2);
     if (e->side2) cudaStreamDestroy(e->side2);
-    if (e->side) cudaStreamDestroy(e->side);
-    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->side) { splitk_release_for_stream(e->side); cudaStreamDestroy(e->side); }
+    if (e->stream) { splitk_release_for_stream(e->stream); cudaStreamDestroy(e->stream); }
     delete e;
 }
 
@@ -489,6 +569,7 @@ extern "C" int ftcf_gptneox_set_option(ftcf_gptneox* e, const char* name, int va
     else if (n == "fused_ln") e->opt_fused_ln = value;
     else if (n == "kv_prefetch") e->opt_kv_prefetch = value;
     else if (n == "pro_ctas") e->opt_pro_ctas = value;
+    else if (n == "tp_fused") e->opt_tp_fused = value;
     else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_option: unknown option %s", name);
     e->drop_graphs();   // anything captured may be stale
     return FTCF_OK;
@@ -622,7 +703,7 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
                 mp.inv_sqrt_dh = 1.f / std::sqrt((float)dh);
                 return ftcf_mmha_decode(&mp, st);
             };
-            FTCF_TRY(run_layer(e, l, B, attn));
+            FTCF_TRY(run_layer(e, l, B, attn, e->t > 1));
         }
     }
     // the LM head stays on the streaming kernel up to 32 rows (1 GB of fp16 weights, 6.9 TB/s there)
@@ -811,6 +892,16 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     }
     memset(e->host_hist, 0, (size_t)max_len * sizeof(int32_t));   // the previous request has drained (forward ends with a sync)
 
+    if (e->tp_fused) {
+        // exchange counters restart with the request (every rank's earlier pushes were consumed before its previous request
+        // returned).  A peer's first push of THIS request follows its prefill, whose all-reduces need this rank's, which follow
+        // this memset in stream order; without a prefill a one-int all-reduce provides the same ordering.
+        FTCF_CUDA_CHECK(cudaMemsetAsync(static_cast<char*>(e->tp_area) + e->tp_data_bytes, 0, 4 * 128, st));
+        if (!has_prefill) FTCF_NCCL_CHECK(g_nccl.AllReduce(s.counters, s.counters, 1, /*ncclInt32*/ 2, NCCL_SUM, e->comm, st));
+        e->tpx.step = s.step;
+        e->tpx.step_base = has_prefill ? S + 1 : S;      // the first loop iteration that runs the layers
+    }
+
     ftcf_sampling_params sp{};
     sp.logits = e->logits.as<float>(); sp.output_ids = s.out_ids; sp.seq_len = s.seq_len; sp.finished = s.finished;
     sp.cum_log_probs = s.cum_log; sp.input_len = s.input_len; sp.top_k = s.top_k; sp.top_p = s.top_p;
@@ -874,7 +965,7 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     char keybuf[320];
     snprintf(keybuf, sizeof(keybuf), "B%d S%d M%d k%d t%d r%d p%d l%p s%p n%d/%d kv%p x%p sm%p lg%p f%d g%lld", B, S, max_len, max_top_k,
              (int)any_temp, (int)any_rep + 2 * (int)any_topp, sp.want_probs, (const void*)sp.optional_last_tokens, (const void*)sp.stop_words,
-             sp.n_last, sp.n_stop, e->kv.p, e->x.p, e->small.p, e->logits.p, (int)e->fused_on,
+             sp.n_last, sp.n_stop, e->kv.p, e->x.p, e->small.p, e->logits.p, (int)e->fused_on + 2 * (int)(e->tp_fused && e->opt_tp_fused),
              g_capture_generation.load(std::memory_order_relaxed));
     const std::string key(keybuf);
 

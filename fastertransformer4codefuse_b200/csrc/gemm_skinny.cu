@@ -23,25 +23,6 @@ namespace ftcf {
 
 enum { EPI_W8 = 0, EPI_F16 = 1, EPI_F32 = 2 };
 
-__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                          uint32_t b1)
-{
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
-// four biased bytes -> (b0-128, b1-128) and (b2-128, b3-128) as half2 bit patterns
-__device__ __forceinline__ void u8x4_to_h2x2(uint32_t w, uint32_t& lo, uint32_t& hi)
-{
-    lo = __byte_perm(w, 0x64646464u, 0x4140);
-    hi = __byte_perm(w, 0x64646464u, 0x4342);
-    const uint32_t magic = 0x64806480u;   // 1152.0 = 1024 + 128, twice
-    asm("sub.f16x2 %0, %1, %2;" : "=r"(lo) : "r"(lo), "r"(magic));
-    asm("sub.f16x2 %0, %1, %2;" : "=r"(hi) : "r"(hi), "r"(magic));
-}
-
 __device__ __forceinline__ int cw_of(int warp) { return warp - 1; }   // consumer-warp index (warp 0 is the producer)
 __device__ __forceinline__ uint32_t u4_get(const uint4& v, int i)
 {
@@ -67,19 +48,6 @@ constexpr int STAGES = 4;
 constexpr int THREADS = 288;             // warp 0: TMA producer, warps 1..8: consumers
 using namespace tma;
 }  // namespace sk
-
-// Fused prologue of the decode layer (m <= 4 tokens): the CTA builds its own copy of the GEMM input in shared memory,
-//   r = ((add_ffn + add_attn) + add_bias) + x       (the PREVIOUS layer's parallel-residual add, add_residual_kernels.cu:116-176;
-//                                                    skipped when add_ffn == NULL)
-//   a = LayerNorm(r; gamma, beta)                   (layernorm_kernels.cu:158-286: fp32 statistics, half2 normalisation)
-// instead of reading what a residual kernel and a LayerNorm kernel wrote: two launches (and their kernel boundaries, ~5 us of
-// idle HBM each) leave the critical path of every layer.  Every CTA recomputes the same 10 KB row (L2 hits); CTA 0 stores r.
-struct SkPro {
-    const __half *x, *add_ffn, *add_attn, *add_bias, *gamma, *beta;
-    __half* x_out;
-    float eps;
-    int cta_hint;
-};
 
 // Pipelined skinny GEMM.  One CTA owns the contiguous feature rows [r0, r1) and all of k.
 //   producer      : one thread issues four TMA boxes (32 rows x 128 bytes, SWIZZLE_128B) per stage, 4 stages = 64 KB in flight
@@ -447,38 +415,7 @@ static SkShape skinny_shape(int n, int k_bytes, int m_groups, bool three_per_sm,
     return sh;
 }
 
-// split-K scratch: a small pool of (partials, tickets) slots handed out round-robin, so that GEMMs running concurrently on two
-// streams (FFN2 and O of one layer) never share one.  Reserved up front: cudaMalloc is not allowed during stream capture.
-namespace {
-constexpr int kPoolSlots = 8;
-constexpr size_t kPartElems = (size_t)4 * 32 * 9472;     // ksplit x m x n
-constexpr int kTicketsPerSlot = 4096;
-float* g_pool_part = nullptr;
-int* g_pool_tickets = nullptr;
-std::atomic<unsigned> g_pool_next{0};
-}  // namespace
-// one (partials, tickets) slot of the pool, or false when it is not reserved / too small (callers then do not split)
-bool splitk_scratch_acquire(size_t part_elems, int tickets_needed, float** part, int** tickets)
-{
-    if (g_pool_part == nullptr || part_elems > kPartElems || tickets_needed > kTicketsPerSlot) return false;
-    const unsigned slot = g_pool_next.fetch_add(1) % kPoolSlots;
-    *part = g_pool_part + (size_t)slot * kPartElems;
-    *tickets = g_pool_tickets + (size_t)slot * kTicketsPerSlot;
-    return true;
-}
-
-int skinny_reserve_scratch()
-{
-    if (g_pool_part != nullptr) return FTCF_OK;
-    float* pp = nullptr;
-    int* tt = nullptr;
-    FTCF_CUDA_CHECK(cudaMalloc(&pp, kPoolSlots * kPartElems * sizeof(float)));
-    FTCF_CUDA_CHECK(cudaMalloc(&tt, (size_t)kPoolSlots * kTicketsPerSlot * sizeof(int)));
-    FTCF_CUDA_CHECK(cudaMemset(tt, 0, (size_t)kPoolSlots * kTicketsPerSlot * sizeof(int)));
-    g_pool_tickets = tt;
-    g_pool_part = pp;
-    return FTCF_OK;
-}
+bool splitk_scratch_acquire(cudaStream_t st, size_t part_elems, int tickets_needed, float** part, int** tickets);   // gemm_decode.cu
 
 template <typename WT, int EPI>
 static int launch_skinny(const void* x, const void* w, const void* scale, const void* bias, void* y, int m, int n, int k,
@@ -492,23 +429,7 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
     SkShape sh = skinny_shape(n, k * (int)sizeof(WT), m_groups, mt == 1 && pro == nullptr, pro != nullptr ? pro->cta_hint : 0);
     float* part = nullptr;
     int* tickets = nullptr;
-    if (sh.ksplit > 1) {
-        if (g_pool_part == nullptr) {
-            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-            if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
-                const int rc = skinny_reserve_scratch();
-                if (rc != FTCF_OK) return rc;
-            }
-        }
-        const bool fits = g_pool_part != nullptr && (size_t)sh.ksplit * m * n <= kPartElems && ceil_div(n, sh.box_rows) * m_groups <= kTicketsPerSlot;
-        if (!fits) {
-            sh.ksplit = 1;
-        } else {
-            const unsigned slot = g_pool_next.fetch_add(1) % kPoolSlots;
-            part = g_pool_part + (size_t)slot * kPartElems;
-            tickets = g_pool_tickets + (size_t)slot * kTicketsPerSlot;
-        }
-    }
+    if (sh.ksplit > 1 && !splitk_scratch_acquire(st, (size_t)sh.ksplit * m * n, ceil_div(n, sh.box_rows) * m_groups, &part, &tickets)) sh.ksplit = 1;
     const int rows_per_cta = sh.rows_per_cta;
     const uint8_t* next_w = nullptr;
     int next_n = 0, next_row_bytes = 0, next_rpc = 1;

@@ -19,11 +19,11 @@
 //   * fp16 weights (int8_mode = 0, LM head): same pipeline, A comes from shared memory through a UMMA descriptor.
 #include <algorithm>
 
-#include "tma_utils.cuh"
+#include "umma.cuh"
 
 namespace ftcf {
 
-bool splitk_scratch_acquire(size_t part_elems, int tickets_needed, float** part, int** tickets);   // gemm_skinny.cu
+bool splitk_scratch_acquire(cudaStream_t st, size_t part_elems, int tickets_needed, float** part, int** tickets);   // gemm_decode.cu
 std::atomic<int> g_tc_ksplit{1};   // tunable "tc_ksplit": k-splits for decode-size launches of the tcgen05 GEMM
 
 namespace tc {
@@ -33,82 +33,8 @@ constexpr int kConvWarps = 8;
 constexpr int kTileM = 128;            // output features per CTA (UMMA M)
 constexpr int kAStages = 4;            // TMEM A-operand stages (u8 path), 64 columns each
 constexpr uint32_t kTmemCols = 512;
-using tma::smem_u32;
-using tma::mbar_init;
-using tma::mbar_arrive;
-using tma::mbar_arrive_expect_tx;
-using tma::mbar_wait;
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) { tma::load_2d(smem_dst, map, bar, c0, c1); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem desc]
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// D[tmem] (+)= A[smem desc] . B[smem desc]
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// K-major operand tile in shared memory, rows of 128 bytes, SWIZZLE_128B, 8-row groups 1024 bytes apart
-// (cute::UMMA::SmemDescriptor: start >> 4 in [0,14), LBO in [16,30), SBO in [32,46), version 1 in [46,48), layout in [61,64)).
-__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;            // LBO: unused for swizzled K-major
-    d |= (uint64_t)(1024 >> 4) << 32;  // SBO
-    d |= (uint64_t)1 << 46;            // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;            // SWIZZLE_128B
-    return d;
-}
-// kind::f16, A = B = fp16, D = fp32, both K-major, M = 128, N = n  (cute::UMMA::InstrDescriptor bit layout)
-__device__ __forceinline__ uint32_t umma_idesc_f16(int n)
-{
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-}
-
-__device__ __forceinline__ void u8x4_to_h2x2(uint32_t w, uint32_t& lo, uint32_t& hi)
-{
-    lo = __byte_perm(w, 0x64646464u, 0x4140);
-    hi = __byte_perm(w, 0x64646464u, 0x4342);
-    const uint32_t magic = 0x64806480u;
-    asm("sub.f16x2 %0, %1, %2;" : "=r"(lo) : "r"(lo), "r"(magic));
-    asm("sub.f16x2 %0, %1, %2;" : "=r"(hi) : "r"(hi), "r"(magic));
-}
-
-__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
-        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
-        "r"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
+constexpr int kGroupM = 16;           // token tiles per rasterisation group
+using namespace umma;
 enum { EPI_W8 = 0, EPI_F16 = 1, EPI_F32 = 2 };
 
 struct Args {
@@ -140,7 +66,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     __shared__ uint32_t s_tmem_base;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * kTileM, m0 = blockIdx.y * NT;
+    // Grouped rasterisation of the 1-D grid: consecutive CTAs (= the CTAs that run together) cover kGroupM token tiles x a run of
+    // feature tiles, so one wave re-uses each weight tile kGroupM times and each activation tile ~148 / kGroupM times out of L2.
+    // (Round 1 ran feature-tile-major: every token tile streamed the whole weight matrix from DRAM again -- ncu: 729 MB read for
+    // a 105 MB matrix at T = 1024.)
+    const int tiles_n = (args.n + kTileM - 1) / kTileM, tiles_m = (args.m + NT - 1) / NT;
+    int tile_m, tile_n;
+    {
+        const int per_group = kGroupM * tiles_n;
+        const int g = (int)blockIdx.x / per_group, r = (int)blockIdx.x % per_group;
+        const int gm = min(kGroupM, tiles_m - g * kGroupM);      // the last group may be short
+        tile_m = g * kGroupM + r % gm;
+        tile_n = r / gm;
+    }
+    const int n0 = tile_n * kTileM, m0 = tile_m * NT;
     // split-K: this CTA contracts k-blocks [kb0, kb0 + num_kb) only (decode-size launches with few feature tiles: n = 5120
     // gives 40 CTAs for 148 SMs; three k-splits stream the same weights with 120)
     const int kb_all = args.k / BK;
@@ -290,7 +229,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             __threadfence();
             asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight converter / epilogue warps
             if (threadIdx.x == 64) {
-                const int tile_id = (int)blockIdx.x * (int)gridDim.y + (int)blockIdx.y;
+                const int tile_id = (int)blockIdx.x;
                 const int old = atomicAdd(&args.tickets[tile_id], 1);
                 s_last = old == S - 1;
                 if (old == S - 1) args.tickets[tile_id] = 0;
@@ -353,15 +292,15 @@ static int launch(const CUtensorMap& mw, const CUtensorMap& mx, const Args& a, c
         FTCF_CUDA_CHECK(cudaFuncSetAttribute(kern_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid(ceil_div(a.n, kTileM), ceil_div(a.m, NT));
+    dim3 grid(ceil_div(a.n, kTileM) * ceil_div(a.m, NT));
     Args aa = a;
     aa.part = nullptr;
     aa.tickets = nullptr;
-    const int tiles = (int)(grid.x * grid.y), kb_all = a.k / BK;
+    const int tiles = (int)grid.x, kb_all = a.k / BK;
     // (measured on the 13B decode step: batch 32 12.2 -> 10.3 ms with the split, batch 16 8.1 -> 9.2 ms: only above 16 rows)
     if (g_tc_ksplit.load(std::memory_order_relaxed) != 0 && a.m > 16 && tiles * 2 <= 148 && kb_all >= 16) {
         int S = std::min(std::min(148 / tiles, 4), kb_all / 8);
-        if (S >= 2 && splitk_scratch_acquire((size_t)S * a.m * a.n, tiles, &aa.part, &aa.tickets)) grid.z = S;
+        if (S >= 2 && splitk_scratch_acquire(st, (size_t)S * a.m * a.n, tiles, &aa.part, &aa.tickets)) grid.z = S;
     }
     if (grid.z > 1) kern_split<<<grid, kThreads, smem, st>>>(mw, mx, aa);
     else kern<<<grid, kThreads, smem, st>>>(mw, mx, aa);

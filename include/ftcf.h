@@ -107,17 +107,46 @@ int ftcf_gemm_f16_ex(const void* x, const void* w_nk, const void* bias, void* y,
  * in shared memory and the GEMM runs on `a`; x_out (optional) receives r.  Same arithmetic as
  * ftcf_add_bias_attn_ffn_residual (tp = 1) followed by ftcf_layernorm (kernels/add_residual_kernels.cu:116-176,
  * kernels/layernorm_kernels.cu:158-286), without their two launches on the layer's critical path. */
+/* Tensor-parallel exchange fused into the decode GEMMs: replaces the residual kernel + ncclAllReduce of
+ * models/gptneox/GptNeoXDecoder.cc:348-359 (and the one-shot kernel of kernels/custom_ar_kernels.cu:139,202) at decode sizes.
+ * Every rank owns an exchange area that all ranks of the node map (CUDA IPC over NVLink):
+ *   data     [2 slots][2 kinds: 0 attn, 1 ffn][tp source ranks][m_max][h] fp16
+ *   counters [2 slots][2 kinds] uint32, 128 bytes apart, monotonic within a request
+ * Push side (O / FFN2 GEMM of rank r): the epilogue stores each output tile into (slot, kind, source r) of EVERY rank's data
+ * area -- remote stores from the kernel that computed the tile -- then adds 1 to that rank's counter (release, system scope).
+ * Gather side (fused prologue of the next QKV / FFN1 GEMM, or ftcf_tp_gather_residual): waits until its OWN counters reached
+ * uses * tp * tiles, rebuilds every rank's partial  o_r = ((ffn_r + attn_r) + bias) + half(x / tp)  with the reference's fp16 adds
+ * (kernels/add_residual_kernels.cu:116-176), sums the tp partials in rank order in fp32 and rounds once: the all-reduce.
+ * The exchange index g = (*step - step_base) * layer_num + layer is evaluated on the device (one captured graph serves every
+ * token): slot = g & 1, uses = g / 2 + 1. */
+typedef struct {
+    void* peer_data[8];            /* data area of every rank, own rank included (device pointers valid in this process) */
+    uint32_t* peer_counter[8];     /* counter area of every rank */
+    int32_t tp, rank, m_max, h;
+    const int32_t* step;           /* device scalar: the decode loop's step */
+    int32_t step_base, layer_num;
+} ftcf_tp_exchange;
+
 typedef struct {
     const void *x, *add_ffn, *add_attn, *add_bias, *gamma, *beta;   /* fp16: [m,k] [m,k] [m,k] [k] [k] [k] */
     void* x_out;                                                    /* [m,k] fp16 or NULL; must not alias x */
     float eps;
     int32_t cta_hint;   /* 0: automatic; > 0: CTAs this launch should aim for (the engine gives the two GEMMs that start a layer
                            together half of the SM slots each, so that neither queues behind the other) */
+    /* tensor-parallel gather (NULL / 0 when unused): the partials of exchange `tp_layer` replace add_ffn / add_attn */
+    const ftcf_tp_exchange* tp_exchange;
+    int32_t tp_layer;
 } ftcf_ln_prologue;
 int ftcf_gemm_w8a16_ln(const ftcf_ln_prologue* pro, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m,
                        int n, int k, int act, void* stream);
 int ftcf_gemm_f16_ln(const ftcf_ln_prologue* pro, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy,
                      int act, int out_f32, void* stream);
+/* INT8 GEMM whose epilogue pushes the [m, n = h] output into every rank's exchange area (kind 0: O GEMM, 1: FFN2 GEMM) instead
+ * of writing y.  m <= ex->m_max, n == ex->h, k a multiple of 128. */
+int ftcf_gemm_w8a16_tp_push(const void* x, const uint8_t* w_nk, const void* scale, const ftcf_tp_exchange* ex, int kind, int layer,
+                            int m, int n, int k, void* stream);
+/* Stand-alone gather side: x_out[m,h] = all-reduced residual of exchange `layer` (see ftcf_tp_exchange); x is that layer's input. */
+int ftcf_tp_gather_residual(const ftcf_tp_exchange* ex, int layer, const void* x, const void* bias, void* x_out, int m, void* stream);
 
 /* out[k,n] -> out_t[n,k] fp16 transpose (load-time re-layout of fp16 weights to K-major). */
 int ftcf_transpose_f16(const void* in_kn, void* out_nk, int k, int n, void* stream);

@@ -53,11 +53,18 @@ def run(m, reps=10):
 
 
 for m in a.m:
-    for pdl in (0, 1):
-        for ctas in (148, 222, 296, 444):
-            for pf in (0,):
+    if a.impl == 3:
+        for pdl in (1, 0):
+            for ctas, min_kb in ((296, 8), (148, 8), (240, 8), (296, 4), (444, 8), (296, 16)):
                 lib.ftcf_set_tunable(b"pdl", pdl)
-                lib.ftcf_set_tunable(b"skinny_target_ctas", ctas)
-                lib.ftcf_set_tunable(b"skinny_prefetch_rows", pf)
+                lib.ftcf_set_tunable(b"decode_target_ctas", ctas)
+                lib.ftcf_set_tunable(b"decode_min_kb", min_kb)
                 ms, gbs = run(m)
-                print(f"m={m:3d} pdl={pdl} ctas={ctas} prefetch_rows={pf:6d}: {ms:7.3f} ms/token-pass  {gbs:7.1f} GB/s", flush=True)
+                print(f"tcgen05 decode m={m:3d} pdl={pdl} target_ctas={ctas} min_kb={min_kb}: {ms:7.3f} ms/token-pass  {gbs:7.1f} GB/s", flush=True)
+        continue
+    for pdl in (0, 1):
+        for ctas in (148, 296):
+            lib.ftcf_set_tunable(b"pdl", pdl)
+            lib.ftcf_set_tunable(b"skinny_target_ctas", ctas)
+            ms, gbs = run(m)
+            print(f"skinny m={m:3d} pdl={pdl} ctas={ctas}: {ms:7.3f} ms/token-pass  {gbs:7.1f} GB/s", flush=True)
