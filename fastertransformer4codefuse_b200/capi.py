@@ -43,8 +43,8 @@ class SamplingParams(C.Structure):
     ]
 
 
-class PrefetchHint(C.Structure):
-    _fields_ = [("w", C.c_void_p), ("n", C.c_int32), ("row_bytes", C.c_int32)]
+class LaunchHint(C.Structure):
+    _fields_ = [("target_ctas", C.c_int32), ("no_pdl", C.c_int32)]
 
 
 class TpExchange(C.Structure):
@@ -101,6 +101,7 @@ SIGNATURES = {
     "ftcf_set_tunable": (C.c_int, [C.c_char_p, C.c_int]),
     "ftcf_debug_trace_start": (C.c_int, [C.c_uint]),
     "ftcf_debug_trace_stop": (C.c_int, [C.c_void_p, C.c_uint, C.POINTER(C.c_uint)]),
+    "ftcf_debug_decode_probe": (C.c_int, [C.c_void_p]),
     "ftcf_symmetric_quantize_int8_host": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,
                                                     C.c_void_p, C.c_void_p]),
     "ftcf_int8_plain_to_b200_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
@@ -110,9 +111,9 @@ SIGNATURES = {
     "ftcf_gemm_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_void_p]),
     "ftcf_gemm_w8a16_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                     C.c_int, C.c_int, C.POINTER(PrefetchHint), C.c_void_p]),
+                                     C.c_int, C.c_int, C.POINTER(LaunchHint), C.c_void_p]),
     "ftcf_gemm_f16_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                   C.c_int, C.c_int, C.POINTER(PrefetchHint), C.c_void_p]),
+                                   C.c_int, C.c_int, C.POINTER(LaunchHint), C.c_void_p]),
     "ftcf_gemm_w8a16_ln": (C.c_int, [C.POINTER(LnPrologue), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_void_p]),
     "ftcf_gemm_f16_ln": (C.c_int, [C.POINTER(LnPrologue), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -20,11 +20,13 @@
 //     every split writes (max, sum, unnormalised out) and the last CTA to arrive (atomic ticket, self-resetting)
 //     merges them -- no second launch;
 //   * masked pad-gap rows are never loaded.
-#include "common.cuh"
+#include "tma_utils.cuh"
 
 namespace ftcf {
 
 constexpr int MMHA_THREADS = 128;
+constexpr int MMHA_BULK_KEYS = 64;       // keys per CTA of the bulk-staged decode attention
+std::atomic<int> g_mmha_bulk{1};         // tunable "mmha_bulk": bulk-staged decode attention at small batch (0: off)
 constexpr int MMHA_MAX_CHUNK = 4096;
 std::atomic<int> g_mmha_splits{0};       // tunable "mmha_splits": force the split count (0: automatic)
 std::atomic<int> g_mmha_onepass{1};      // tunable "mmha_onepass": one-pass (online softmax) decode attention; 0: the two-pass kernel
@@ -508,6 +510,217 @@ __global__ void __launch_bounds__(MMHA_THREADS, 6) mmha_decode_onepass_kernel(co
     }
 }
 
+// ---------------------------------------------------------------- decode attention, bulk-staged (small batch)
+// At batch <= 8 the kernels above are latency-bound: a CTA walks its keys in dependent rounds of 16 KB, and when the FFN2 GEMM
+// streams at the same time every round queues behind its deep TMA ring (measured in the 13B decode step: 17 us alone, 26-29 us
+// beside the GEMM, on the critical path QKV -> attention -> O of every layer).  Here a CTA owns at most 64 keys of one
+// (sequence, head): ONE thread asks for its whole K tile and V tile with two bulk copies (cp.async.bulk, rows of a (b, h) pair
+// are contiguous in the [B, H, max_len, dh] cache) BEFORE the dependency wait -- earlier positions do not depend on this
+// layer's QKV GEMM -- so every byte the launch needs is in flight at once and has usually landed when q arrives.  Scores,
+// softmax and P.V then run out of shared memory; the split partials are merged by the last arriver as in the kernels above.
+template <int DH>
+__global__ void __launch_bounds__(MMHA_THREADS, 6) mmha_decode_bulk_kernel(const MmhaP params)
+{
+    const ftcf_mmha_params& p = params.p;
+    constexpr int LPR = DH / 8;               // lanes per cache row (16 bytes each)
+    constexpr int NG = MMHA_THREADS / LPR;    // keys handled per pass
+    constexpr int CH = MMHA_BULK_KEYS;
+
+    extern __shared__ __align__(128) uint8_t bulk_smem[];        // [K tile: CH x DH fp16][V tile: CH x DH fp16]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float s_out[NG][DH];
+    __shared__ float s_sc[CH];
+    __shared__ float s_red[32];
+    __shared__ __align__(16) __half s_q[DH];
+    __shared__ __align__(16) __half s_k[DH];
+    __shared__ __align__(16) __half s_v[DH];
+    __shared__ int s_flag;
+
+    const int h = blockIdx.x, b = blockIdx.y, split = blockIdx.z;
+    const int H = p.heads, tid = threadIdx.x;
+    const unsigned long long trc_t0 = trc_now(threadIdx.x == 0);
+    pdl_launch_dependents();
+    // request state (lengths, finished flags) is constant within a decode step: safe to read before the dependency wait
+    if (p.finished != nullptr && p.finished[b]) return;
+    const int tlen = p.seq_len[b];
+    const int total = tlen + 1;
+    const int nact = ceil_div(total, CH);                 // splits that have keys at this step
+    if (split >= nact) return;
+    const int chunk = ceil_div(total, nact);              // <= CH, balanced
+    const int start = split * chunk;
+    const int end = min(start + chunk, total);
+    const int cnt = end - start;
+    const int owner = tlen / chunk;                       // the split that holds the new token
+    const int in_len = p.input_len[b], max_in = p.max_input_len;
+    const int nload = min(end, tlen) - start;             // cached rows of this split (the new token's row comes from qkv)
+
+    __half* kc = static_cast<__half*>(p.k_cache) + ((size_t)b * H + h) * (size_t)p.max_len * DH;
+    __half* vc = static_cast<__half*>(p.v_cache) + ((size_t)b * H + h) * (size_t)p.max_len * DH;
+    const __half* sK = reinterpret_cast<const __half*>(bulk_smem);
+    const __half* sV = sK + CH * DH;
+    if (tid == 0) {
+        tma::mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bytes = nload > 0 ? (uint32_t)nload * DH * 2 : 0u;
+        tma::mbar_arrive_expect_tx(&bar, 2 * bytes);
+        if (nload > 0) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tma::smem_u32(sK)),
+                         "l"(kc + (size_t)start * DH), "r"(bytes), "r"(tma::smem_u32(&bar))
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tma::smem_u32(sV)),
+                         "l"(vc + (size_t)start * DH), "r"(bytes), "r"(tma::smem_u32(&bar))
+                         : "memory");
+        }
+    }
+    pdl_wait();                               // qkv of this layer is complete and visible
+    const unsigned long long trc_t1 = trc_now(threadIdx.x == 0);
+
+    const __half* qkv = static_cast<const __half*>(p.qkv) + (size_t)b * 3 * H * DH;
+    const __half* bias = static_cast<const __half*>(p.qkv_bias);
+    const int li = tid % LPR, gi = tid / LPR;
+    // ---- q (all splits), k / v (owner split): bias, rotary, append to the cache
+    for (int d = tid; d < DH; d += MMHA_THREADS) {
+        const int rot = p.rotary_dim;
+        const int pos = (*p.step - 1) - p.pad_count[b];
+        const int qi = h * DH + d;
+        __half q = qkv[qi];
+        if (bias) q = __hadd(q, bias[qi]);
+        const bool do_rot = d < rot;
+        const int dp = d < (rot >> 1) ? d + (rot >> 1) : d - (rot >> 1);
+        if (do_rot) {
+            __half qp = qkv[h * DH + dp];
+            if (bias) qp = __hadd(qp, bias[h * DH + dp]);
+            q = rotary_neox(q, qp, d, rot, pos);
+        }
+        s_q[d] = q;
+        if (split == owner) {
+            const int ki = H * DH + qi, vi = 2 * H * DH + qi;
+            __half k = qkv[ki], v = qkv[vi];
+            if (bias) {
+                k = __hadd(k, bias[ki]);
+                v = __hadd(v, bias[vi]);
+            }
+            if (do_rot) {
+                __half kp = qkv[H * DH + h * DH + dp];
+                if (bias) kp = __hadd(kp, bias[H * DH + h * DH + dp]);
+                k = rotary_neox(k, kp, d, rot, pos);
+            }
+            s_k[d] = k;
+            s_v[d] = v;
+            kc[(size_t)tlen * DH + d] = k;
+            vc[(size_t)tlen * DH + d] = v;
+        }
+    }
+    __syncthreads();                          // s_q / s_k / s_v and the barrier initialisation are visible to all threads
+    float q[8];
+    {
+        const uint4 qv = *reinterpret_cast<const uint4*>(&s_q[li * 8]);
+        const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(qh[i]);
+            q[2 * i] = f.x;
+            q[2 * i + 1] = f.y;
+        }
+    }
+    tma::mbar_wait(&bar, 0);                  // both tiles have landed
+    const unsigned long long trc_t2 = trc_now(threadIdx.x == 0);
+
+    // ---- scores
+    for (int j0 = 0; j0 < cnt; j0 += NG) {
+        const int j = j0 + gi, pos = start + j;
+        const bool valid = j < cnt && !(pos >= in_len && pos < max_in);
+        float dot = 0.f;
+        if (valid) {
+            const uint4 kv = *reinterpret_cast<const uint4*>(pos == tlen ? &s_k[li * 8] : &sK[(size_t)j * DH + li * 8]);
+            const __half2* kh = reinterpret_cast<const __half2*>(&kv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(kh[i]);
+                dot = fmaf(q[2 * i], f.x, dot);
+                dot = fmaf(q[2 * i + 1], f.y, dot);
+            }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (li == 0 && j < cnt) s_sc[j] = valid ? dot * p.inv_sqrt_dh : -INFINITY;
+    }
+    __syncthreads();
+    // ---- softmax statistics of this split (cnt <= 64 <= threads)
+    const float scv = tid < cnt ? s_sc[tid] : -INFINITY;
+    const float mx = block_max(scv, s_red);
+    const float ev = (scv == -INFINITY) ? 0.f : __expf(scv - mx);
+    const float sum = block_sum(ev, s_red);
+    if (tid < cnt) s_sc[tid] = ev;
+    __syncthreads();
+    // ---- P.V
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int j = gi; j < cnt; j += NG) {
+        const float pr = s_sc[j];
+        if (pr == 0.f) continue;
+        const uint4 vv = *reinterpret_cast<const uint4*>(start + j == tlen ? &s_v[li * 8] : &sV[(size_t)j * DH + li * 8]);
+        const __half2* vh = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(vh[i]);
+            acc[2 * i] = fmaf(pr, f.x, acc[2 * i]);
+            acc[2 * i + 1] = fmaf(pr, f.y, acc[2 * i + 1]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_out[gi][li * 8 + i] = acc[i];
+    __syncthreads();
+
+    __half* ctx = static_cast<__half*>(p.ctx) + (size_t)b * H * DH + h * DH;
+    float* part = p.partial + ((size_t)(b * H + h) * p.splits + split) * (DH + 2);
+    for (int d = tid; d < DH; d += MMHA_THREADS) {
+        float o = 0.f;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) o += s_out[g][d];
+        if (nact == 1) ctx[d] = __float2half_rn(o * (1.f / (sum + 1e-6f)));
+        else part[d] = o;
+    }
+    if (nact == 1) {
+        if (tid == 0) trc_emit(TRC_MMHA, trc_t0, trc_t1, trc_t2, cnt, 0);
+        return;
+    }
+    if (tid == 0) {
+        part[DH] = mx;
+        part[DH + 1] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int old = atomicAdd(&p.counters[b * H + h], 1);
+        s_flag = (old == nact - 1);
+    }
+    __syncthreads();
+    if (!s_flag) {
+        if (tid == 0) trc_emit(TRC_MMHA, trc_t0, trc_t1, trc_t2, cnt, 0);
+        return;
+    }
+    __threadfence();
+    const float* all = p.partial + (size_t)(b * H + h) * p.splits * (DH + 2);
+    float M = -INFINITY;
+    for (int s2 = 0; s2 < nact; ++s2) M = fmaxf(M, __ldcg(&all[s2 * (DH + 2) + DH]));
+    for (int d = tid; d < DH; d += MMHA_THREADS) {
+        float L = 0.f, O = 0.f;
+        for (int s2 = 0; s2 < nact; ++s2) {
+            const float mi = __ldcg(&all[s2 * (DH + 2) + DH]);
+            const float wgt = (mi == -INFINITY) ? 0.f : __expf(mi - M);
+            L = fmaf(__ldcg(&all[s2 * (DH + 2) + DH + 1]), wgt, L);
+            O = fmaf(__ldcg(&all[s2 * (DH + 2) + d]), wgt, O);
+        }
+        ctx[d] = __float2half_rn(O * (1.f / (L + 1e-6f)));
+    }
+    if (tid == 0) {
+        p.counters[b * H + h] = 0;
+        trc_emit(TRC_MMHA, trc_t0, trc_t1, trc_t2, cnt, 1);
+    }
+}
+
 // L2 prefetch of the cache rows one decode-attention launch will read (every valid slot < seq_len of every sequence and head),
 // launched on a side stream at the START of the layer: the rows travel while the QKV GEMM streams its weights, and the
 // attention kernel -- a chain of dependent load rounds -- then runs on L2 hits.  evict_last so the weight stream (evict_first)
@@ -836,9 +1049,15 @@ prefill_attention_kernel(const __half* __restrict__ q, const __half* __restrict_
 
 using namespace ftcf;
 
+static bool mmha_bulk_applies(int batch, int heads, int dh)
+{
+    return g_mmha_bulk.load() != 0 && batch * heads <= 320 && (dh == 64 || dh == 128);
+}
+
 extern "C" int ftcf_mmha_choose_splits(int batch, int heads, int max_len)
 {
     const int ctas = batch * heads;
+    if (g_mmha_splits.load() == 0 && mmha_bulk_applies(batch, heads, 128)) return ceil_div(max_len, MMHA_BULK_KEYS);
     int splits = ceil_div(148 * 4, ctas > 0 ? ctas : 1);
     if (g_mmha_splits.load() > 0) splits = g_mmha_splits.load();   // experiment hook
     const int by_len = ceil_div(max_len, 128);          // at least 128 keys per split
@@ -874,6 +1093,20 @@ extern "C" int ftcf_mmha_decode(const ftcf_mmha_params* p, void* stream)
     // one pass where the launch is a single wave of CTAs (measured, 13B decode step: batch 8 -5 %, batch 1 equal, batch 32 +3 %)
     const bool onepass = g_mmha_onepass.load() == 2 || (g_mmha_onepass.load() != 0 && p->batch * p->heads <= 148 * 4);
     const bool pdl = g_mmha_pdl.load() != 0;
+    // small batch, enough splits that no CTA gets more than 64 keys: the bulk-staged kernel
+    if (mmha_bulk_applies(p->batch, p->heads, p->dh) && ceil_div(p->max_len, p->splits) <= MMHA_BULK_KEYS) {
+        const size_t smem = (size_t)2 * MMHA_BULK_KEYS * p->dh * sizeof(__half);
+        if (p->dh == 128) {
+            static std::atomic<int> cfg128{0};
+            if (!cfg128.exchange(1)) FTCF_CUDA_CHECK(cudaFuncSetAttribute(mmha_decode_bulk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            lerr = launch_pdl(mmha_decode_bulk_kernel<128>, grid, dim3(MMHA_THREADS), smem, as_stream(stream), mp);
+        } else {
+            lerr = launch_pdl(mmha_decode_bulk_kernel<64>, grid, dim3(MMHA_THREADS), smem, as_stream(stream), mp);
+        }
+        FTCF_REQUIRE(lerr == cudaSuccess, FTCF_ERR_CUDA, "mmha (bulk) launch failed: %s", cudaGetErrorString(lerr));
+        FTCF_LAUNCH_CHECK();
+        return FTCF_OK;
+    }
     switch (p->dh) {
         case 64: lerr = onepass ? launch_pdl_if(pdl, mmha_decode_onepass_kernel<64>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp)
                                 : launch_pdl_if(pdl, mmha_decode_kernel<64>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;

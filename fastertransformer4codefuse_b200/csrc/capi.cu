@@ -27,9 +27,9 @@ void set_error(const char* fmt, ...)
 
 // implemented in gemm_skinny.cu / gemm_tcgen05.cu
 int gemm_w8a16_skinny(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n, int k,
-                      int act, const ftcf_prefetch_hint* next, cudaStream_t st);
+                      int act, const ftcf_launch_hint* hint, cudaStream_t st);
 int gemm_f16_skinny(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
-                    int out_f32, const ftcf_prefetch_hint* next, cudaStream_t st);
+                    int out_f32, const ftcf_launch_hint* hint, cudaStream_t st);
 int gemm_w8a16_skinny_ln(const ftcf_ln_prologue& pro, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n, int k,
                          int act, cudaStream_t st);
 int gemm_f16_skinny_ln(const ftcf_ln_prologue& pro, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
@@ -40,13 +40,13 @@ int gemm_f16_tcgen05(const void* x, const void* w_nk, const void* bias, void* y,
                      int out_f32, cudaStream_t st);
 bool gemm_tcgen05_supported(int m, int n, int k, int elem_bytes);
 int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n, int k, int act,
-                      const SkPro* pro, cudaStream_t st, const ftcf_tp_exchange* push = nullptr, int push_kind = 0, int push_layer = 0);
+                      const SkPro* pro, cudaStream_t st, const ftcf_tp_exchange* push = nullptr, int push_kind = 0, int push_layer = 0,
+                      const ftcf_launch_hint* hint = nullptr);
 bool gemm_decode_supported(int m, int n, int k);
-extern std::atomic<int> g_dg_target_ctas, g_dg_min_kb, g_dg_evict_first;
+extern std::atomic<int> g_dg_target_ctas, g_dg_min_kb, g_dg_evict_first, g_dg_max_stages, g_dg_fake_tiled;
 std::atomic<int> g_decode_impl{3};   // tunable "decode_impl": 3 = tcgen05 decode GEMM for int8 at m <= 32 (default), 1 = round-1 streaming mma.sync kernel
-extern std::atomic<int> g_prefill_mma, g_mmha_onepass, g_mmha_splits;
-extern std::atomic<int> g_mmha_pdl, g_mmha_prefetch, g_sk_carveout, g_sk_ksplit, g_sk_evict_first, g_sk_even_rows, g_tc_ksplit;
-extern std::atomic<int> g_sk_target_ctas, g_sk_prefetch_rows, g_sk_pf_ahead;
+extern std::atomic<int> g_prefill_mma, g_mmha_onepass, g_mmha_splits, g_mmha_bulk;
+extern std::atomic<int> g_mmha_pdl, g_mmha_prefetch, g_sk_carveout, g_sk_evict_first, g_tc_ksplit, g_sk_target_ctas;
 
 }  // namespace ftcf
 
@@ -63,22 +63,21 @@ extern "C" int ftcf_set_tunable(const char* name, int value)
     g_capture_generation.fetch_add(1, std::memory_order_relaxed);   // captured launches may depend on any of these
     if (n == "pdl") g_pdl_enabled.store(value);
     else if (n == "skinny_target_ctas") { FTCF_REQUIRE(value >= 0, FTCF_ERR_INVALID, "skinny_target_ctas %d", value); g_sk_target_ctas.store(value); }
-    else if (n == "skinny_ksplit") g_sk_ksplit.store(value);
     else if (n == "skinny_evict_first") g_sk_evict_first.store(value);
-    else if (n == "skinny_even_rows") g_sk_even_rows.store(value);
     else if (n == "tc_ksplit") g_tc_ksplit.store(value);
-    else if (n == "skinny_prefetch_rows") { FTCF_REQUIRE(value >= 0, FTCF_ERR_INVALID, "skinny_prefetch_rows %d", value); g_sk_prefetch_rows.store(value); }
-    else if (n == "skinny_pf_ahead") g_sk_pf_ahead.store(value);
     else if (n == "mmha_pdl") g_mmha_pdl.store(value);
     else if (n == "prefill_mma") g_prefill_mma.store(value);
     else if (n == "mmha_onepass") g_mmha_onepass.store(value);
     else if (n == "mmha_splits") g_mmha_splits.store(value);
+    else if (n == "mmha_bulk") g_mmha_bulk.store(value);
     else if (n == "mmha_prefetch") g_mmha_prefetch.store(value);
     else if (n == "skinny_carveout") g_sk_carveout.store(value);
     else if (n == "decode_target_ctas") g_dg_target_ctas.store(value);
     else if (n == "decode_min_kb") g_dg_min_kb.store(value);
     else if (n == "decode_evict_first") g_dg_evict_first.store(value);
     else if (n == "decode_impl") g_decode_impl.store(value);
+    else if (n == "decode_max_stages") g_dg_max_stages.store(value);
+    else if (n == "decode_fake_tiled") g_dg_fake_tiled.store(value);
     else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_tunable: unknown tunable %s", name);
     return FTCF_OK;
 }
@@ -103,6 +102,11 @@ static int trace_install_all(TraceRec* buf, unsigned* cnt, unsigned cap)
     if (rc == FTCF_OK) rc = trace_install_sampling(buf, cnt, cap);
     return rc;
 }
+
+namespace ftcf { int decode_probe_install(long long* dev_buf); }
+// Debug: install (or remove, NULL) a device buffer of 64 x 8 int64 that CTA (0,0,0) of every decode-GEMM launch fills with
+// per-K-step clock stamps (see gemm_decode.cu).
+extern "C" int ftcf_debug_decode_probe(void* dev_buf) { return decode_probe_install(static_cast<long long*>(dev_buf)); }
 
 extern "C" int ftcf_debug_trace_start(unsigned capacity)
 {
@@ -153,18 +157,18 @@ extern "C" int ftcf_device_check(void)
 static constexpr int kSkinnyMaxM = 11;   // fp16 weights only: above it the tcgen05 kernel takes over
 
 extern "C" int ftcf_gemm_w8a16_ex(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n,
-                                  int k, int act, int impl, const ftcf_prefetch_hint* next, void* stream)
+                                  int k, int act, int impl, const ftcf_launch_hint* hint, void* stream)
 {
     FTCF_REQUIRE(x && w_nk && scale && y, FTCF_ERR_INVALID, "gemm_w8a16: null operand");
     FTCF_REQUIRE(act == 0 || act == 1, FTCF_ERR_INVALID, "gemm_w8a16: act %d", act);
     cudaStream_t st = as_stream(stream);
-    if (impl == 1) return gemm_w8a16_skinny(x, w_nk, scale, bias, y, m, n, k, act, next, st);
+    if (impl == 1) return gemm_w8a16_skinny(x, w_nk, scale, bias, y, m, n, k, act, hint, st);
     if (impl == 2) return gemm_w8a16_tcgen05(x, w_nk, scale, bias, y, m, n, k, act, st);
-    if (impl == 3) return gemm_w8a16_decode(x, w_nk, scale, bias, y, m, n, k, act, nullptr, st);
+    if (impl == 3) return gemm_w8a16_decode(x, w_nk, scale, bias, y, m, n, k, act, nullptr, st, nullptr, 0, 0, hint);
     if (g_decode_impl.load(std::memory_order_relaxed) == 3 && gemm_decode_supported(m, n, k))
-        return gemm_w8a16_decode(x, w_nk, scale, bias, y, m, n, k, act, nullptr, st);
+        return gemm_w8a16_decode(x, w_nk, scale, bias, y, m, n, k, act, nullptr, st, nullptr, 0, 0, hint);
     if (m > kSkinnyMaxM && gemm_tcgen05_supported(m, n, k, 1)) return gemm_w8a16_tcgen05(x, w_nk, scale, bias, y, m, n, k, act, st);
-    return gemm_w8a16_skinny(x, w_nk, scale, bias, y, m, n, k, act, next, st);
+    return gemm_w8a16_skinny(x, w_nk, scale, bias, y, m, n, k, act, hint, st);
 }
 
 extern "C" int ftcf_gemm_w8a16(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n,
@@ -217,17 +221,17 @@ extern "C" int ftcf_gemm_f16_ln(const ftcf_ln_prologue* pro, const void* w_nk, c
 }
 
 extern "C" int ftcf_gemm_f16_ex(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
-                                int out_f32, int impl, const ftcf_prefetch_hint* next, void* stream)
+                                int out_f32, int impl, const ftcf_launch_hint* hint, void* stream)
 {
     FTCF_REQUIRE(x && w_nk && y, FTCF_ERR_INVALID, "gemm_f16: null operand");
     FTCF_REQUIRE(act == 0 || act == 1, FTCF_ERR_INVALID, "gemm_f16: act %d", act);
     FTCF_REQUIRE(ldy >= n, FTCF_ERR_INVALID, "gemm_f16: ldy %d < n %d", ldy, n);
     cudaStream_t st = as_stream(stream);
-    if (impl == 1) return gemm_f16_skinny(x, w_nk, bias, y, m, n, k, ldy, act, out_f32, next, st);
+    if (impl == 1) return gemm_f16_skinny(x, w_nk, bias, y, m, n, k, ldy, act, out_f32, hint, st);
     if (impl == 2) return gemm_f16_tcgen05(x, w_nk, bias, y, m, n, k, ldy, act, out_f32, st);
     if (m > kSkinnyMaxM && gemm_tcgen05_supported(m, n, k, 2))
         return gemm_f16_tcgen05(x, w_nk, bias, y, m, n, k, ldy, act, out_f32, st);
-    return gemm_f16_skinny(x, w_nk, bias, y, m, n, k, ldy, act, out_f32, next, st);
+    return gemm_f16_skinny(x, w_nk, bias, y, m, n, k, ldy, act, out_f32, hint, st);
 }
 
 extern "C" int ftcf_gemm_f16(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,

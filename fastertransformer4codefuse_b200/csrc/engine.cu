@@ -181,6 +181,8 @@ struct ftcf_gptneox {
 
     // options
     int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_kv_prefetch = 0, opt_pro_ctas = 148, opt_tp_fused = 1;
+    // CTA targets of the four decode GEMMs of a layer in the fused path (0: pro_ctas for QKV / FFN1, the kernel's default for O / FFN2)
+    int opt_qkv_ctas = 0, opt_ffn1_ctas = 0, opt_o_ctas = 0, opt_ffn2_ctas = 0, opt_ffn2_no_pdl = 0;
 
     // request-sized buffers (grow only)
     DevBuf kv, x, x2, n1, n2, qkv, qbuf, ctx, attn, inter, ffn, logits, logits_local, logits_gather, samp_ws, small, mmha_part,
@@ -570,6 +572,11 @@ extern "C" int ftcf_gptneox_set_option(ftcf_gptneox* e, const char* name, int va
     else if (n == "kv_prefetch") e->opt_kv_prefetch = value;
     else if (n == "pro_ctas") e->opt_pro_ctas = value;
     else if (n == "tp_fused") e->opt_tp_fused = value;
+    else if (n == "qkv_ctas") e->opt_qkv_ctas = value;
+    else if (n == "ffn1_ctas") e->opt_ffn1_ctas = value;
+    else if (n == "o_ctas") e->opt_o_ctas = value;
+    else if (n == "ffn2_ctas") e->opt_ffn2_ctas = value;
+    else if (n == "ffn2_no_pdl") e->opt_ffn2_no_pdl = value;
     else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_option: unknown option %s", name);
     e->drop_graphs();   // anything captured may be stale
     return FTCF_OK;
@@ -618,6 +625,8 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
             pro.gamma = g; pro.beta = b; pro.eps = c.layernorm_eps;
             // QKV and FFN1 start together: half of the SM slots each (measured: QKV otherwise queues behind FFN1's CTAs for ~25 us)
             pro.cta_hint = (l < c.layer_num && e->opt_two_branch) ? e->opt_pro_ctas : 0;
+            if (l < c.layer_num && store && e->opt_qkv_ctas > 0) pro.cta_hint = e->opt_qkv_ctas;       // store == the QKV prologue
+            if (l < c.layer_num && !store && e->opt_ffn1_ctas > 0) pro.cta_hint = e->opt_ffn1_ctas;
             if (l == 0) {
                 pro.x = xb[0];
             } else {
@@ -658,7 +667,8 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
             const ftcf_ln_prologue p2 = prologue(l, lw.ln2_g, lw.ln2_b, false);
             if (w8) {
                 FTCF_TRY(ftcf_gemm_w8a16_ln(&p2, static_cast<const uint8_t*>(lw.w[2]), lw.scale[2], lw.ffn1_b, e->inter.p, B, e->inter_l, e->h, 1, sb));
-                FTCF_TRY(ftcf_gemm_w8a16(e->inter.p, static_cast<const uint8_t*>(lw.w[3]), lw.scale[3], nullptr, ffn[l & 1], B, e->h, e->inter_l, 0, 1, sb));
+                const ftcf_launch_hint h2{e->opt_ffn2_ctas, e->opt_ffn2_no_pdl};
+                FTCF_TRY(ftcf_gemm_w8a16_ex(e->inter.p, static_cast<const uint8_t*>(lw.w[3]), lw.scale[3], nullptr, ffn[l & 1], B, e->h, e->inter_l, 0, e->opt_gemm_impl, &h2, sb));
             } else {
                 FTCF_TRY(ftcf_gemm_f16_ln(&p2, lw.w[2], lw.ffn1_b, e->inter.p, B, e->inter_l, e->h, e->inter_l, 1, 0, sb));
                 FTCF_TRY(ftcf_gemm_f16(e->inter.p, lw.w[3], nullptr, ffn[l & 1], B, e->h, e->inter_l, e->h, 0, 0, 1, sb));
@@ -668,7 +678,8 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
             if (w8) FTCF_TRY(ftcf_gemm_w8a16_ln(&p1, static_cast<const uint8_t*>(lw.w[0]), lw.scale[0], nullptr, e->qkv.p, B, 3 * e->hl, e->h, 0, st));
             else FTCF_TRY(ftcf_gemm_f16_ln(&p1, lw.w[0], nullptr, e->qkv.p, B, 3 * e->hl, e->h, 3 * e->hl, 0, 0, st));
             FTCF_TRY(ftcf_mmha_decode(&mp, st));
-            if (w8) FTCF_TRY(ftcf_gemm_w8a16(e->ctx.p, static_cast<const uint8_t*>(lw.w[1]), lw.scale[1], nullptr, attn[l & 1], B, e->h, e->hl, 0, 1, st));
+            const ftcf_launch_hint ho{e->opt_o_ctas, 0};
+            if (w8) FTCF_TRY(ftcf_gemm_w8a16_ex(e->ctx.p, static_cast<const uint8_t*>(lw.w[1]), lw.scale[1], nullptr, attn[l & 1], B, e->h, e->hl, 0, e->opt_gemm_impl, &ho, st));
             else FTCF_TRY(ftcf_gemm_f16(e->ctx.p, lw.w[1], nullptr, attn[l & 1], B, e->h, e->hl, e->h, 0, 0, 1, st));
             if (e->opt_two_branch) FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join, 0));
             if (kvpf) FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join2, 0));

@@ -32,6 +32,8 @@ namespace ftcf {
 std::atomic<int> g_dg_target_ctas{296};   // tunable "decode_target_ctas": CTAs a launch aims for (k-splits fill up to it)
 std::atomic<int> g_dg_min_kb{8};          // tunable "decode_min_kb": fewest 128-byte K steps a k-split may get
 std::atomic<int> g_dg_evict_first{1};     // tunable "decode_evict_first"
+std::atomic<int> g_dg_fake_tiled{0};      // EXPERIMENT (timing only, wrong results): weight stages fetched as contiguous 16 KB runs
+std::atomic<int> g_dg_max_stages{6};      // tunable "decode_max_stages": cap on the weight-ring depth (16 KB per stage)
 
 // ---- split-K scratch: one (partials, tickets) slot per STREAM.  Launches on one stream are ordered (a PDL-launched successor
 // touches its scratch only after griddepcontrol.wait), so one slot per stream is enough, and engines / threads that use
@@ -90,6 +92,10 @@ bool splitk_scratch_acquire(cudaStream_t st, size_t part_elems, int tickets_need
 namespace dg {
 using namespace umma;
 
+// Debug: per-K-step clock stamps of CTA (0,0,0) -- converter warp 2 [0..4] and the MMA warp [5..7] -- written when a buffer is
+// installed with ftcf_debug_decode_probe (tools/decode_gemm_probe.py).  8 x int64 per K step.
+__device__ long long* g_probe = nullptr;
+
 constexpr int kThreads = 320;          // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2..9: convert + epilogue
 constexpr int kConvWarps = 8;
 constexpr int kTileM = 128;            // output features per CTA (UMMA M)
@@ -109,6 +115,8 @@ struct Args {
     int* tickets;     // one self-resetting counter per feature tile
     int stages;       // depth of the weight ring (<= kMaxStages)
     int evict_first;
+    int fake_tiled;
+    const uint8_t* w_raw;
     SkPro pro;        // PRO only
     ftcf_tp_exchange push;   // push.tp > 1: the epilogue stores the output into every rank's exchange area instead of y
     int push_kind, push_layer;
@@ -147,15 +155,44 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_w_empty[s], kConvWarps * 32);
+            mbar_init(&bar_w_empty[s], kConvWarps);      // one arrival per converter WARP
             mbar_init(&bar_x_empty[s], 1);
         }
         for (int s = 0; s < kAStages; ++s) {
-            mbar_init(&bar_a_full[s], kConvWarps * 32);
+            mbar_init(&bar_a_full[s], kConvWarps);
             mbar_init(&bar_a_empty[s], 1);
         }
         mbar_init(&bar_d_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // Bulk-copy / MMA / commit instructions take uniform operands: they are issued by the elected lane of a warp that runs its
+    // role in warp-uniform control flow (tma::elect_one_sync), never from behind `if (lane == 0)`.
+    auto load_w = [&](int kb, int s) {
+        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+        if (args.fake_tiled) {
+            const uint8_t* src = args.w_raw + ((size_t)blockIdx.x * kb_all + kb0 + kb) * W_BYTES;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(st)),
+                         "l"(src), "r"(W_BYTES), "r"(smem_u32(&bar_full[s])) : "memory");
+        } else if (args.evict_first) {
+            tma::load_2d_hint(st, &map_w, &bar_full[s], (kb0 + kb) * BK, n0, tma::l2_policy_evict_first());
+        } else {
+            tma::load_2d(st, &map_w, &bar_full[s], (kb0 + kb) * BK, n0);
+        }
+    };
+    const int pre = min(stages, num_kb);
+    if (warp == 0) {
+        __syncwarp();      // the barrier initialisation above (lane 0) is visible to whichever lane is elected
+        // The first ring fill goes out NOW, before this CTA has its tensor memory: weights are constants, so a CTA that was
+        // launched early (programmatic dependent launch) streams them while the previous kernel still runs -- even while it
+        // waits in tcgen05.alloc for that kernel's CTAs on this SM to release their columns.
+        if (tma::elect_one_sync()) {
+            tma::prefetch_map(&map_w);
+            for (int kb = 0; kb < pre; ++kb) {
+                mbar_arrive_expect_tx(&bar_full[kb], STAGE_BYTES);
+                load_w(kb, kb);
+            }
+        }
+        __syncwarp();
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(kTmemCols)
@@ -166,61 +203,59 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
+    long long* const probe = (blockIdx.x == 0 && blockIdx.z == 0) ? g_probe : nullptr;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            tma::prefetch_map(&map_w);
-            if constexpr (!PRO) tma::prefetch_map(&map_x);
-            const uint64_t pol = tma::l2_policy_evict_first();
-            auto load_w = [&](int kb, int s) {
-                uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-                if (args.evict_first) tma::load_2d_hint(st, &map_w, &bar_full[s], (kb0 + kb) * BK, n0, pol);
-                else tma::load_2d(st, &map_w, &bar_full[s], (kb0 + kb) * BK, n0);
-            };
-            auto load_x = [&](int kb, int s) {
-                uint8_t* st = smem + (size_t)s * STAGE_BYTES + W_BYTES;
-                tma::load_2d(st, &map_x, &bar_full[s], (kb0 + kb) * BK, 0);
-                tma::load_2d(st + NT * 128, &map_x, &bar_full[s], (kb0 + kb) * BK + 64, 0);
-            };
-            // the first ring fill: weights are constants, so they are requested before the previous kernel has finished;
-            // the activations it produces are requested after the dependency wait
-            const int pre = min(stages, num_kb);
-            for (int kb = 0; kb < pre; ++kb) {
-                mbar_arrive_expect_tx(&bar_full[kb], STAGE_BYTES);
-                load_w(kb, kb);
-            }
-            pdl_wait();
-            if constexpr (!PRO)
+        // ================= TMA producer (whole warp in lock step, one elected lane issues) =================
+        auto load_x = [&](int kb, int s) {
+            uint8_t* st = smem + (size_t)s * STAGE_BYTES + W_BYTES;
+            tma::load_2d(st, &map_x, &bar_full[s], (kb0 + kb) * BK, 0);
+            tma::load_2d(st + NT * 128, &map_x, &bar_full[s], (kb0 + kb) * BK + 64, 0);
+        };
+        // (the weights of the first ring fill were requested at kernel entry;) the activations the previous kernel produces
+        // are requested after the dependency wait
+        pdl_wait();
+        if constexpr (!PRO) {
+            if (tma::elect_one_sync()) {
+                tma::prefetch_map(&map_x);
                 for (int kb = 0; kb < pre; ++kb) load_x(kb, kb);
-            for (int kb = pre; kb < num_kb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (kb / stages) & 1;
-                mbar_wait(&bar_w_empty[s], ph ^ 1);
-                if constexpr (!PRO) mbar_wait(&bar_x_empty[s], ph ^ 1);
+            }
+            __syncwarp();
+        }
+        // ring positions advance with running counters: `stages` is a launch parameter, and kb % stages / kb / stages on a run-time
+        // divisor cost ~240 cycles per K step (measured with tools/decode_gemm_probe.py)
+        int s = pre == stages ? 0 : pre;
+        uint32_t ph = pre == stages ? 1 : 0;
+        for (int kb = pre; kb < num_kb; ++kb) {
+            mbar_wait(&bar_w_empty[s], ph ^ 1);
+            if constexpr (!PRO) mbar_wait(&bar_x_empty[s], ph ^ 1);
+            if (tma::elect_one_sync()) {
                 mbar_arrive_expect_tx(&bar_full[s], STAGE_BYTES);
                 load_w(kb, s);
                 if constexpr (!PRO) load_x(kb, s);
             }
+            __syncwarp();
+            if (++s == stages) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(NT);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (kb / stages) & 1;
-                const int as = kb % kAStages;
-                const uint32_t aph = (kb / kAStages) & 1;
-                uint32_t xaddr;
-                if constexpr (PRO) {
-                    xaddr = smem_u32(slab0 + (size_t)as * X_BYTES);
-                } else {
-                    mbar_wait(&bar_full[s], ph);      // the activation slab of this K step has landed
-                    xaddr = smem_u32(smem + (size_t)s * STAGE_BYTES + W_BYTES);
-                }
-                mbar_wait(&bar_a_full[as], aph);
-                tc_fence_after();
+        // ================= MMA issuer (whole warp waits, one elected lane issues MMAs and commits) =================
+        const uint32_t idesc = umma_idesc_f16(NT);
+        int s = 0, as = 0;
+        uint32_t ph = 0, aph = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            uint32_t xaddr;
+            if constexpr (PRO) {
+                xaddr = smem_u32(slab0 + (size_t)as * X_BYTES);
+            } else {
+                mbar_wait(&bar_full[s], ph);      // the activation slab of this K step has landed
+                xaddr = smem_u32(smem + (size_t)s * STAGE_BYTES + W_BYTES);
+            }
+            const bool prb = probe != nullptr && lane == 0 && kb < 64;
+            if (prb) probe[kb * 8 + 5] = clock64();
+            mbar_wait(&bar_a_full[as], aph);
+            if (prb) probe[kb * 8 + 6] = clock64();
+            tc_fence_after();
+            if (tma::elect_one_sync()) {
 #pragma unroll
                 for (int ks = 0; ks < BK / 16; ++ks) {
                     const uint32_t a_t = tmem + A_COL + as * 64 + ks * 8;
@@ -229,8 +264,16 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                 }
                 tc_commit(&bar_a_empty[as]);
                 if constexpr (!PRO) tc_commit(&bar_x_empty[s]);
+                if (kb == num_kb - 1) tc_commit(&bar_d_full);
             }
-            tc_commit(&bar_d_full);   // (with num_kb == 0 nothing was issued: the commit completes at once)
+            __syncwarp();
+            if (prb) probe[kb * 8 + 7] = clock64();
+            if (++s == stages) { s = 0; ph ^= 1; }
+            if (++as == kAStages) { as = 0; aph ^= 1; }
+        }
+        if (num_kb == 0) {
+            if (tma::elect_one_sync()) tc_commit(&bar_d_full);   // nothing was issued: the commit completes at once
+            __syncwarp();
         }
     } else {
         // ================= converter warps (u8 -> fp16 -> TMEM), then epilogue =================
@@ -323,21 +366,23 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
+        int s = 0, as = 0;
+        uint32_t ph = 0, aph = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % stages;
-            const uint32_t ph = (kb / stages) & 1;
-            const int as = kb % kAStages;
-            const uint32_t aph = (kb / kAStages) & 1;
+            const bool prb = probe != nullptr && warp == 2 && lane == 0 && kb < 64;
+            if (prb) probe[kb * 8 + 0] = clock64();
             mbar_wait(&bar_full[s], ph);
+            if (prb) probe[kb * 8 + 1] = clock64();
             if (kb == 0) trc_t2 = trc_now(trc_who);
-            const uint8_t* wt = smem + (size_t)s * STAGE_BYTES + row * 128;
+            const uint32_t wt = smem_u32(smem + (size_t)s * STAGE_BYTES + row * 128);
             uint4 v[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int chunk = (hf * 4 + c) ^ (row & 7);      // SWIZZLE_128B: 16-byte chunk index XOR row % 8
-                v[c] = *reinterpret_cast<const uint4*>(wt + chunk * 16);
+                v[c] = tma::lds_128(wt + chunk * 16);
             }
-            mbar_arrive(&bar_w_empty[s]);                        // the u8 tile is in registers now
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_w_empty[s]);         // every lane of this warp has issued its reads of the u8 tile
             uint32_t r[32];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -346,7 +391,9 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                 u8x4_to_h2x2(v[c].z, r[c * 8 + 4], r[c * 8 + 5]);
                 u8x4_to_h2x2(v[c].w, r[c * 8 + 6], r[c * 8 + 7]);
             }
+            if (prb) probe[kb * 8 + 2] = clock64();
             mbar_wait(&bar_a_empty[as], aph ^ 1);
+            if (prb) probe[kb * 8 + 3] = clock64();
             tc_fence_after();
             if constexpr (PRO) {
                 // activation slab of this K step: m rows x 256 bytes out of xs, 16-byte chunks placed as the UMMA descriptor
@@ -362,7 +409,11 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             tmem_st_x32(tmem + ((uint32_t)(q * 32) << 16) + A_COL + as * 64 + hf * 32, r);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mbar_arrive(&bar_a_full[as]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_a_full[as]);
+            if (prb) probe[kb * 8 + 4] = clock64();
+            if (++s == stages) { s = 0; ph ^= 1; }
+            if (++as == kAStages) { as = 0; aph ^= 1; }
         }
         // ---- epilogue: this warp owns accumulator rows [32q, 32q+32) and token columns [hf*NT/2, (hf+1)*NT/2)
         if constexpr (!PRO) pdl_wait();          // y may still be read by the previous kernel
@@ -457,13 +508,19 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 
 FTCF_TRACE_INSTALLER(trace_install_gemm_decode)
 
+int decode_probe_install(long long* dev_buf)
+{
+    FTCF_CUDA_CHECK(cudaMemcpyToSymbol(dg::g_probe, &dev_buf, sizeof(dev_buf)));
+    return FTCF_OK;
+}
+
 bool gemm_decode_supported(int m, int n, int k)
 {
     return m >= 1 && m <= 32 && n >= 1 && k >= dg::BK && k % dg::BK == 0;
 }
 
 template <int NT, bool PRO>
-static int launch_decode(const CUtensorMap& mw, const CUtensorMap& mx, dg::Args a, dim3 grid, size_t smem, cudaStream_t st)
+static int launch_decode(const CUtensorMap& mw, const CUtensorMap& mx, dg::Args a, dim3 grid, size_t smem, cudaStream_t st, bool pdl)
 {
     auto kern = dg::gemm_decode_kernel<NT, PRO>;
     static std::atomic<size_t> configured{0};      // per instantiation; the attribute is per function (and per device context)
@@ -472,7 +529,7 @@ static int launch_decode(const CUtensorMap& mw, const CUtensorMap& mx, dg::Args 
         FTCF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         configured.store(smem, std::memory_order_relaxed);
     }
-    const cudaError_t err = launch_pdl(kern, grid, dim3(dg::kThreads), smem, st, mw, mx, a);
+    const cudaError_t err = launch_pdl_if(pdl, kern, grid, dim3(dg::kThreads), smem, st, mw, mx, a);
     FTCF_REQUIRE(err == cudaSuccess, FTCF_ERR_CUDA, "decode gemm launch failed: %s", cudaGetErrorString(err));
     FTCF_LAUNCH_CHECK();
     return FTCF_OK;
@@ -480,13 +537,16 @@ static int launch_decode(const CUtensorMap& mw, const CUtensorMap& mx, dg::Args 
 
 // x == nullptr selects the fused-prologue variant (pro != nullptr, m <= 4)
 int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n, int k, int act,
-                      const SkPro* pro, cudaStream_t st, const ftcf_tp_exchange* push, int push_kind, int push_layer)
+                      const SkPro* pro, cudaStream_t st, const ftcf_tp_exchange* push, int push_kind, int push_layer, const ftcf_launch_hint* hint)
 {
     FTCF_REQUIRE(gemm_decode_supported(m, n, k), FTCF_ERR_UNSUPPORTED, "decode gemm: m=%d (1..32), k=%d (multiple of 128)", m, k);
     const int nt = m <= 16 ? 16 : 32;
     const int tiles = ceil_div(n, dg::kTileM), kb_all = k / dg::BK;
     // k-splits: fill the co-resident CTA slots (2 per SM), but leave every split enough K steps to amortise its pipeline fill
-    const int target = (pro != nullptr && pro->cta_hint > 0) ? pro->cta_hint : g_dg_target_ctas.load(std::memory_order_relaxed);
+    int target = g_dg_target_ctas.load(std::memory_order_relaxed);
+    if (pro != nullptr && pro->cta_hint > 0) target = pro->cta_hint;
+    if (hint != nullptr && hint->target_ctas > 0) target = hint->target_ctas;
+    const bool pdl = hint == nullptr || hint->no_pdl == 0;
     int S = std::max(1, std::min(target / tiles, kb_all / std::max(1, g_dg_min_kb.load(std::memory_order_relaxed))));
     S = std::min(S, 16);
     dg::Args a{};
@@ -495,6 +555,8 @@ int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, con
     a.y = static_cast<__half*>(y);
     a.m = m; a.n = n; a.k = k; a.ldy = n; a.act = act;
     a.evict_first = g_dg_evict_first.load(std::memory_order_relaxed);
+    a.fake_tiled = (n % 128 == 0) ? g_dg_fake_tiled.load(std::memory_order_relaxed) : 0;
+    a.w_raw = w_nk;
     if (push != nullptr) {
         FTCF_REQUIRE(push->tp > 1 && push->tp <= 8 && push->rank >= 0 && push->rank < push->tp && m <= push->m_max && n == push->h &&
                          (push_kind == 0 || push_kind == 1) && push->step != nullptr,
@@ -520,12 +582,11 @@ int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, con
     } else {
         per_stage += x_bytes;
     }
-    int stages = fixed < budget ? (int)((budget - fixed) / per_stage) : 0;
-    stages = std::min(std::min(stages, dg::kMaxStages), std::max(kb_per, 2));
-    if (stages < 3) {                                   // the prologue rows crowd the ring out: one CTA per SM then
-        stages = (int)std::min<size_t>(dg::kMaxStages, (220 * 1024 - fixed) / per_stage);
-        FTCF_REQUIRE(stages >= 2, FTCF_ERR_UNSUPPORTED, "decode gemm: m=%d k=%d does not fit shared memory", m, k);
-    }
+    int fit = fixed < budget ? (int)((budget - fixed) / per_stage) : 0;
+    if (fit < 3) fit = (int)((220 * 1024 - fixed) / per_stage);      // the prologue rows crowd the ring out: one CTA per SM then
+    FTCF_REQUIRE(fit >= 2, FTCF_ERR_UNSUPPORTED, "decode gemm: m=%d k=%d does not fit shared memory", m, k);
+    const int cap = std::min(dg::kMaxStages, std::max(2, g_dg_max_stages.load(std::memory_order_relaxed)));
+    const int stages = std::min(std::min(fit, cap), std::max(kb_per, 2));
     a.stages = stages;
     const size_t smem = fixed + (size_t)stages * per_stage;
     CUtensorMap mw, mx;
@@ -538,9 +599,9 @@ int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, con
         mx = mw;   // unused
     }
     const dim3 grid(tiles, 1, S);
-    if (pro != nullptr) return launch_decode<16, true>(mw, mx, a, grid, smem, st);
-    if (nt == 16) return launch_decode<16, false>(mw, mx, a, grid, smem, st);
-    return launch_decode<32, false>(mw, mx, a, grid, smem, st);
+    if (pro != nullptr) return launch_decode<16, true>(mw, mx, a, grid, smem, st, pdl);
+    if (nt == 16) return launch_decode<16, false>(mw, mx, a, grid, smem, st, pdl);
+    return launch_decode<32, false>(mw, mx, a, grid, smem, st, pdl);
 }
 
 }  // namespace ftcf

@@ -15,6 +15,8 @@
 //     fragments come from ONE contiguous 16-byte piece of a weight row (no shuffles, no transposes);
 //   * cross-warp (split-k inside the CTA) reduction through shared memory in a fixed order -> deterministic;
 //   * epilogue: per-column scale (fp32), bias, tanh-GELU, fp16 (or fp32 logits) store.
+// Since round 2 the INT8 decode GEMMs run on tcgen05 (gemm_decode.cu); this kernel streams the fp16 weights (LM head, int8_mode = 0
+// layers) and stays selectable for INT8 (impl = 1) as the A/B baseline.
 #include <algorithm>
 
 #include "tma_utils.cuh"
@@ -29,15 +31,10 @@ __device__ __forceinline__ uint32_t u4_get(const uint4& v, int i)
     return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
 }
 
-// tunables (ftcf_set_tunable): how many CTAs one launch aims for (all of them co-resident, so HBM is shared evenly and the
-// next kernel's CTAs fit beside them) -- see launch_skinny.
-std::atomic<int> g_sk_target_ctas{0};    // 0: automatic (see skinny_shape)
-std::atomic<int> g_sk_even_rows{0};      // 1: rows per pass (TMA box height 8..32) chosen so that all co-resident CTAs get equal shares; measured: per-shape +3 %, but the extra CTAs starve the attention kernel of SM slots (decode step +20 %), so off
-std::atomic<int> g_sk_ksplit{0};         // 1: split k when a launch has fewer than half as many CTAs as slots (measured: no gain, off)
+// tunables (ftcf_set_tunable)
+std::atomic<int> g_sk_target_ctas{0};    // CTAs one launch aims for, all co-resident (0: automatic, see skinny_shape)
 std::atomic<int> g_sk_evict_first{1};    // weight tiles are loaded with an L2 evict_first policy
 std::atomic<int> g_sk_carveout{1};       // 1: ask for the maximum shared-memory carveout (3 CTAs per SM fit)
-std::atomic<int> g_sk_pf_ahead{0};       // stages (16 KB each) of its OWN stream a producer keeps prefetched in L2 beyond the shared-memory ring
-std::atomic<int> g_sk_prefetch_rows{0};  // rows of each NEXT-kernel CTA slice that a finishing CTA prefetches into L2; measured on B200: it does not pay (gcb_2.log), so 0 = off
 
 namespace sk {
 constexpr int ROWS = 32;                 // output features per pass (two 16-row MMA tiles)
@@ -57,15 +54,11 @@ using namespace tma;
 //                   128-byte swizzle), converts
 //                   u8 -> fp16 in registers and issues mma.sync.m16n8k16 against the token fragments (read through L1);
 //   end of a pass : the four k-step warps of a tile are summed through shared memory in a fixed order, epilogue, store.
-// Split-K (gridDim.z > 1; used when a GEMM has fewer row tiles than the GPU has CTA slots, i.e. n <= ~9000): CTA (x, y, z)
-// streams k-chunk z of its rows and stores fp32 partial sums; the LAST CTA to arrive for a row tile (ticket counter) adds the
-// gridDim.z partials in the fixed order 0, 1, ... and runs the epilogue -- deterministic, no second launch.
 template <typename WT, int MT, int EPI, bool PRO = false>
 __global__ void __launch_bounds__(sk::THREADS, (MT <= 2 ? 2 : 1))
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, const __half* __restrict__ x, const __half* __restrict__ scale,
                    const __half* __restrict__ bias, void* __restrict__ y, int m, int n, int k, int ldy, int act, int rows_per_cta,
-                   const uint8_t* __restrict__ next_w, int next_n, int next_row_bytes, int next_rows_per_cta, int next_pf_rows, int pf_ahead,
-                   float* __restrict__ part, int* __restrict__ tickets, int evict_first, int R)
+                   int evict_first, int R)
 {
     using namespace sk;
     constexpr int EPC = 16 / sizeof(WT);   // k-elements per 16-byte chunk
@@ -83,16 +76,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(n, r0 + rows_per_cta);
     const int m0 = blockIdx.y * NT;
     const int row_bytes = k * (int)sizeof(WT);
-    const int chunks_all = (row_bytes + CHUNK - 1) / CHUNK;
-    const int cps = (chunks_all + (int)gridDim.z - 1) / (int)gridDim.z;          // chunks per k-split
-    const int kc0 = (int)blockIdx.z * cps, kc1 = min(chunks_all, kc0 + cps);
-    const int chunks = max(kc1 - kc0, 0);
+    const int chunks = (row_bytes + CHUNK - 1) / CHUNK;
+    const int kc0 = 0, kc1 = chunks;
     // R = rows per pass = height of the TMA box (<= ROWS; each box still owns a 32-row slot of the stage so that the
     // 128-byte swizzle pattern stays 1024-byte aligned): lets the host cut n into equal shares for ALL co-resident CTAs
     const int passes = (r1 - r0 + R - 1) / R;
     const int total = passes * chunks;       // stages this CTA streams
-    __shared__ int s_last;
-
     pdl_launch_dependents();
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -104,51 +93,29 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
     __syncthreads();
 
     if (warp == 0) {
-        // ================= producer =================
-        if (lane == 0) {
-            prefetch_map(&map_w);
+        // ================= producer (warp-uniform loop, the elected lane issues: no per-instruction waterfall) =================
+        {
+            if (elect_one_sync()) prefetch_map(&map_w);
             const uint64_t pol = l2_policy_evict_first();
-            // L2 prefetch window: while this CTA's consumers still wait for the previous kernel (PDL) -- and HBM would idle
-            // through the kernel boundary with only the 64 KB ring requested -- the producer keeps asking L2 for the stages
-            // that follow the ring, so the ring later refills at L2 latency.
             for (int i = 0; i < total; ++i) {
-                if (i == STAGES && pf_ahead > 0) {
-                    // the ring is full and this thread is about to block until the consumers start (they wait for the previous
-                    // kernel): one burst of L2 prefetches for the stages that follow the ring.  (A rolling window was measured
-                    // to cost steady-state bandwidth: every byte then crosses L2 twice.)
-                    for (int pf_i = STAGES; pf_i < min(total, STAGES + pf_ahead); ++pf_i) {
-                        const int ppass = pf_i / chunks, pkc = kc0 + pf_i % chunks;
-                        const int pn = min(4, (row_bytes - pkc * CHUNK) / 128);
-                        for (int j = 0; j < pn; ++j) prefetch_2d(&map_w, (pkc * CHUNK + j * 128) / (int)sizeof(WT), r0 + ppass * R);
-                    }
-                }
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
                 const int pass = i / chunks, kc = kc0 + i % chunks;
                 const int nsub = min(4, (row_bytes - kc * CHUNK) / 128);     // 128-byte k-steps in this chunk
                 mbar_wait(&bar_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&bar_full[s], (uint32_t)(nsub * R * 128));
-                if (evict_first) {
-                    for (int j = 0; j < nsub; ++j)
-                        load_2d_hint(sk_smem + (size_t)s * STAGE_BYTES + j * SUB_BYTES, &map_w, &bar_full[s],
-                                     (kc * CHUNK + j * 128) / (int)sizeof(WT), r0 + pass * R, pol);
-                } else {
-                    for (int j = 0; j < nsub; ++j)
-                        load_2d(sk_smem + (size_t)s * STAGE_BYTES + j * SUB_BYTES, &map_w, &bar_full[s],
-                                (kc * CHUNK + j * 128) / (int)sizeof(WT), r0 + pass * R);
+                if (elect_one_sync()) {
+                    mbar_arrive_expect_tx(&bar_full[s], (uint32_t)(nsub * R * 128));
+                    if (evict_first) {
+                        for (int j = 0; j < nsub; ++j)
+                            load_2d_hint(sk_smem + (size_t)s * STAGE_BYTES + j * SUB_BYTES, &map_w, &bar_full[s],
+                                         (kc * CHUNK + j * 128) / (int)sizeof(WT), r0 + pass * R, pol);
+                    } else {
+                        for (int j = 0; j < nsub; ++j)
+                            load_2d(sk_smem + (size_t)s * STAGE_BYTES + j * SUB_BYTES, &map_w, &bar_full[s],
+                                    (kc * CHUNK + j * 128) / (int)sizeof(WT), r0 + pass * R);
+                    }
                 }
-            }
-        }
-        // Tail prefetch: everything this CTA needs has been requested; queue L2 prefetches for the HEAD of the next GEMM's
-        // weight stream (the first rows of the slices its CTAs will own) behind them, so HBM keeps working through this
-        // kernel's drain, the launch gap and the next kernel's ramp-up instead of idling (~8 us per boundary otherwise).
-        if (next_w != nullptr && blockIdx.y == 0) {
-            __syncwarp();
-            const int next_ctas = (next_n + next_rows_per_cta - 1) / next_rows_per_cta;
-            for (int c = blockIdx.x; c < next_ctas; c += gridDim.x) {
-                const int nr0 = c * next_rows_per_cta, nr1 = min(next_n, nr0 + min(next_rows_per_cta, next_pf_rows));
-                for (int row = nr0 + lane; row < nr1; row += 32)
-                    l2_prefetch_bulk(next_w + (size_t)row * next_row_bytes, (uint32_t)next_row_bytes);
+                __syncwarp();
             }
         }
         return;
@@ -315,46 +282,14 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int p0 = r0 + pass * R;
         const int pr1 = min(r1, p0 + R);          // rows of this pass that belong to this CTA
-        const int S = (int)gridDim.z;
-        bool finish = true;
-        if (S > 1) {
-            // publish this k-split's partial tile, take a ticket; only the last arriver goes on
-            for (int o = threadIdx.x - 32; o < ROWS * NT; o += 256) {
-                const int f = o % ROWS, tok = o / ROWS;
-                const int col = p0 + f, row = m0 + tok;
-                if (col >= pr1 || row >= m) continue;
-                const int tl = f >> 4, fl = f & 15;
-                float v = red[tl * 4 + 0][tok][fl] + red[tl * 4 + 1][tok][fl];
-                v += red[tl * 4 + 2][tok][fl];
-                v += red[tl * 4 + 3][tok][fl];
-                part[((size_t)blockIdx.z * m + row) * n + col] = v;
-            }
-            __threadfence();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (threadIdx.x == 32) {
-                const int tile_id = (p0 / R) * (int)gridDim.y + (int)blockIdx.y;
-                const int old = atomicAdd(&tickets[tile_id], 1);
-                s_last = old == S - 1;
-                if (old == S - 1) tickets[tile_id] = 0;      // self-resetting for the next launch that uses this slot
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            finish = s_last != 0;
-            if (finish) __threadfence();
-        }
-        for (int o = threadIdx.x - 32; o < ROWS * NT && finish; o += 256) {
+        for (int o = threadIdx.x - 32; o < ROWS * NT; o += 256) {
             const int f = o % ROWS, tok = o / ROWS;
             const int col = p0 + f, row = m0 + tok;
             if (col >= pr1 || row >= m) continue;
             const int tl = f >> 4, fl = f & 15;
-            float v;
-            if (S > 1) {
-                v = __ldcg(&part[(size_t)row * n + col]);
-                for (int z = 1; z < S; ++z) v += __ldcg(&part[((size_t)z * m + row) * n + col]);
-            } else {
-                v = red[tl * 4 + 0][tok][fl] + red[tl * 4 + 1][tok][fl];
-                v += red[tl * 4 + 2][tok][fl];
-                v += red[tl * 4 + 3][tok][fl];
-            }
+            float v = red[tl * 4 + 0][tok][fl] + red[tl * 4 + 1][tok][fl];
+            v += red[tl * 4 + 2][tok][fl];
+            v += red[tl * 4 + 3][tok][fl];
             if constexpr (EPI == EPI_W8) {
                 v *= __half2float(scale[col]);
                 if (bias != nullptr) v += __half2float(bias[col]);
@@ -376,73 +311,39 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const SkPro pro, c
 
 FTCF_TRACE_INSTALLER(trace_install_gemm_skinny)
 
-// ---- launch shape: how many CTAs, how many 32-row passes each, how many k-splits
-// A CTA's consumer pipeline sustains ~20-25 GB/s (measured: 148 CTAs alone reach 3.7 TB/s, 296 reach 5.7 TB/s), so a launch
-// needs at least two CTAs on every SM, all co-resident and with equal work: `slots` = CTAs that fit at once (3 per SM for the
-// one-token-group int8 / fp16 kernel, 2 otherwise); GEMMs with few row tiles (n = 5120: 160) are split along k.
+// ---- launch shape: how many CTAs, how many 32-row passes each
+// A CTA's mma.sync consumer pipeline sustains ~20-25 GB/s (measured: 148 CTAs alone reach 3.7 TB/s, 296 reach 5.7 TB/s), so a
+// launch wants two CTAs on every SM, all co-resident, with whole 32-row tiles each.  (Measured and dropped in round 1: three
+// CTAs per SM, equal-share box heights, k-splits, L2 prefetch of the next GEMM's weights.)
 struct SkShape {
-    int rows_per_cta, ctas_x, ksplit, box_rows;
+    int rows_per_cta, ctas_x;
 };
-static SkShape skinny_shape(int n, int k_bytes, int m_groups, bool three_per_sm, int hint = 0)
+static SkShape skinny_shape(int n, int m_groups, int hint)
 {
     const int forced = hint > 0 ? hint : g_sk_target_ctas.load(std::memory_order_relaxed);
-    (void)three_per_sm;   // 3 CTAs per SM was measured slower: the block scheduler then loads the SMs unevenly (240 CTAs: 3 + 3 + ... )
     const int slots = forced > 0 ? forced : 296;
-    // equal shares: the smallest pass count whose per-pass height fits a box (<= 32 rows, multiple of 4)
-    const int per_cta_max = std::max(1, slots / m_groups);
-    int passes = 1, R = sk::ROWS;
-    for (;; ++passes) {
-        const int want = ceil_div(n, per_cta_max * passes);        // rows per pass if every slot got an equal share
-        R = std::max(8, ((want + 3) / 4) * 4);
-        if (R <= sk::ROWS) break;
-    }
-    if (g_sk_even_rows.load(std::memory_order_relaxed) == 0) {      // old rule: whole 32-row tiles
-        const int tiles = ceil_div(n, sk::ROWS);
-        passes = ceil_div(tiles * m_groups, slots);
-        R = sk::ROWS;
-    }
+    const int tiles = ceil_div(n, sk::ROWS);
+    const int passes = ceil_div(tiles * m_groups, slots);
     SkShape sh;
-    sh.box_rows = R;
-    sh.rows_per_cta = passes * R;
+    sh.rows_per_cta = passes * sk::ROWS;
     sh.ctas_x = ceil_div(n, sh.rows_per_cta);
-    sh.ksplit = 1;
-    const int chunks = ceil_div(k_bytes, sk::CHUNK);
-    if (g_sk_ksplit.load(std::memory_order_relaxed) != 0 && passes == 1) {
-        int s2 = slots / (sh.ctas_x * m_groups);
-        s2 = std::min(s2, std::min(4, chunks / 5));          // at least 5 stages per CTA
-        if (s2 >= 2) sh.ksplit = s2;
-    }
     return sh;
 }
 
-bool splitk_scratch_acquire(cudaStream_t st, size_t part_elems, int tickets_needed, float** part, int** tickets);   // gemm_decode.cu
-
 template <typename WT, int EPI>
 static int launch_skinny(const void* x, const void* w, const void* scale, const void* bias, void* y, int m, int n, int k,
-                         int ldy, int act, const ftcf_prefetch_hint* next, cudaStream_t st, const SkPro* pro = nullptr)
+                         int ldy, int act, const ftcf_launch_hint* hint, cudaStream_t st, const SkPro* pro = nullptr)
 {
     constexpr int EPC = 16 / sizeof(WT);
     FTCF_REQUIRE(k % (8 * EPC) == 0, FTCF_ERR_UNSUPPORTED, "skinny gemm: k=%d must be a multiple of %d", k, 8 * EPC);
     FTCF_REQUIRE(m > 0 && n > 0, FTCF_ERR_INVALID, "skinny gemm: empty problem m=%d n=%d", m, n);
     const int mt = m >= 25 ? 4 : ceil_div(m, 8);
     const int m_groups = ceil_div(m, 8 * mt);
-    SkShape sh = skinny_shape(n, k * (int)sizeof(WT), m_groups, mt == 1 && pro == nullptr, pro != nullptr ? pro->cta_hint : 0);
-    float* part = nullptr;
-    int* tickets = nullptr;
-    if (sh.ksplit > 1 && !splitk_scratch_acquire(st, (size_t)sh.ksplit * m * n, ceil_div(n, sh.box_rows) * m_groups, &part, &tickets)) sh.ksplit = 1;
+    const int want = pro != nullptr ? pro->cta_hint : (hint != nullptr ? hint->target_ctas : 0);
+    const SkShape sh = skinny_shape(n, m_groups, want);
     const int rows_per_cta = sh.rows_per_cta;
-    const uint8_t* next_w = nullptr;
-    int next_n = 0, next_row_bytes = 0, next_rpc = 1;
-    const int next_pf = g_sk_prefetch_rows.load(std::memory_order_relaxed);
-    const int pf_ahead = g_sk_pf_ahead.load(std::memory_order_relaxed);
     const int evict_first = g_sk_evict_first.load(std::memory_order_relaxed);
-    if (next != nullptr && next->w != nullptr && next_pf > 0 && next->row_bytes % 16 == 0) {
-        next_w = static_cast<const uint8_t*>(next->w);
-        next_n = next->n;
-        next_row_bytes = next->row_bytes;
-        next_rpc = skinny_shape(next->n, next->row_bytes, 1, true).rows_per_cta;
-    }
-    const dim3 grid(sh.ctas_x, m_groups, sh.ksplit);
+    const dim3 grid(sh.ctas_x, m_groups, 1);
     const dim3 block(sk::THREADS);
     size_t smem = (size_t)sk::STAGES * sk::STAGE_BYTES + 1024;
     SkPro prov{};
@@ -457,23 +358,24 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
     const __half* xs = static_cast<const __half*>(x);
     CUtensorMap mw;
     {
-        const int rc = make_tensor_map_2d(&mw, w, n, k, (int)sizeof(WT), sh.box_rows);
+        const int rc = make_tensor_map_2d(&mw, w, n, k, (int)sizeof(WT), sk::ROWS);
         if (rc != FTCF_OK) return rc;
     }
     const __half* sc = static_cast<const __half*>(scale);
     const __half* bs = static_cast<const __half*>(bias);
+    const bool pdl = hint == nullptr || hint->no_pdl == 0;
     cudaError_t err = cudaSuccess;
 #define FTCF_SK_(MT_, PRO_)                                                                                             \
     do {                                                                                                                \
-        static size_t configured = 0;                                                                                   \
-        if (configured < smem) {                                                                                        \
+        static std::atomic<size_t> configured{0};                                                                       \
+        if (configured.load(std::memory_order_relaxed) < smem) {                                                        \
             err = cudaFuncSetAttribute(gemm_skinny_kernel<WT, MT_, EPI, PRO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (err == cudaSuccess && g_sk_carveout.load())                                                             \
                 err = cudaFuncSetAttribute(gemm_skinny_kernel<WT, MT_, EPI, PRO_>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared); \
-            configured = smem;                                                                                          \
+            configured.store(smem, std::memory_order_relaxed);                                                          \
         }                                                                                                               \
         if (err == cudaSuccess)                                                                                         \
-            err = launch_pdl(gemm_skinny_kernel<WT, MT_, EPI, PRO_>, grid, block, smem, st, mw, prov, xs, sc, bs, y, m, n, k, ldy, act, rows_per_cta, next_w, next_n, next_row_bytes, next_rpc, next_pf, pf_ahead, part, tickets, evict_first, sh.box_rows); \
+            err = launch_pdl_if(pdl, gemm_skinny_kernel<WT, MT_, EPI, PRO_>, grid, block, smem, st, mw, prov, xs, sc, bs, y, m, n, k, ldy, act, rows_per_cta, evict_first, sk::ROWS); \
     } while (0)
 #define FTCF_SK(MT_) FTCF_SK_(MT_, false)
     if (pro != nullptr) {
@@ -496,16 +398,16 @@ static int launch_skinny(const void* x, const void* w, const void* scale, const 
 }
 
 int gemm_w8a16_skinny(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n, int k,
-                      int act, const ftcf_prefetch_hint* next, cudaStream_t st)
+                      int act, const ftcf_launch_hint* hint, cudaStream_t st)
 {
-    return launch_skinny<uint8_t, EPI_W8>(x, w_nk, scale, bias, y, m, n, k, n, act, next, st);
+    return launch_skinny<uint8_t, EPI_W8>(x, w_nk, scale, bias, y, m, n, k, n, act, hint, st);
 }
 
 int gemm_f16_skinny(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
-                    int out_f32, const ftcf_prefetch_hint* next, cudaStream_t st)
+                    int out_f32, const ftcf_launch_hint* hint, cudaStream_t st)
 {
-    if (out_f32) return launch_skinny<__half, EPI_F32>(x, w_nk, nullptr, bias, y, m, n, k, ldy, act, next, st);
-    return launch_skinny<__half, EPI_F16>(x, w_nk, nullptr, bias, y, m, n, k, ldy, act, next, st);
+    if (out_f32) return launch_skinny<__half, EPI_F32>(x, w_nk, nullptr, bias, y, m, n, k, ldy, act, hint, st);
+    return launch_skinny<__half, EPI_F16>(x, w_nk, nullptr, bias, y, m, n, k, ldy, act, hint, st);
 }
 
 static SkPro to_skpro(const ftcf_ln_prologue& p)

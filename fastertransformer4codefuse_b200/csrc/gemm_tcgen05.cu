@@ -91,11 +91,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_w_empty[s], W8 ? kConvWarps * 32 : 1);
+            mbar_init(&bar_w_empty[s], W8 ? kConvWarps : 1);   // one arrival per converter WARP (per-thread arrivals
+            // serialise on the barrier word: ~2000 cycles per K block, ncu r2c)
             mbar_init(&bar_x_empty[s], 1);
         }
         for (int s = 0; s < kAStages; ++s) {
-            mbar_init(&bar_a_full[s], kConvWarps * 32);
+            mbar_init(&bar_a_full[s], kConvWarps);
             mbar_init(&bar_a_empty[s], 1);
         }
         mbar_init(&bar_d_full, 1);
@@ -111,16 +112,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
 
+    // Single-thread instructions with uniform operands (TMA, tcgen05.mma, tcgen05.commit) are issued by the elected lane of a warp
+    // that runs its role in warp-uniform control flow; behind `if (lane == 0)` every one of them costs a ~120-cycle waterfall loop.
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (tma::elect_one_sync()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&bar_w_empty[s], ph ^ 1);
-                mbar_wait(&bar_x_empty[s], ph ^ 1);
+        }
+        __syncwarp();
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&bar_w_empty[s], ph ^ 1);
+            mbar_wait(&bar_x_empty[s], ph ^ 1);
+            if (tma::elect_one_sync()) {
                 uint8_t* st = smem + (size_t)s * STAGE_BYTES;
                 mbar_arrive_expect_tx(&bar_full[s], STAGE_BYTES);
                 tma_load_2d(st, &map_w, &bar_full[s], (kb0 + kb) * BK, n0);
@@ -128,21 +134,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 for (int xs = 0; xs < XSUB; ++xs)
                     tma_load_2d(st + W_BYTES + xs * NT * 128, &map_x, &bar_full[s], (kb0 + kb) * BK + xs * 64, m0);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(NT);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                const uint32_t st_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                mbar_wait(&bar_full[s], ph);
-                if constexpr (W8) {
-                    const int as = kb % kAStages;
-                    const uint32_t aph = (kb / kAStages) & 1;
-                    mbar_wait(&bar_a_full[as], aph);
-                    tc_fence_after();
+        const uint32_t idesc = umma_idesc_f16(NT);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            const uint32_t st_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
+            mbar_wait(&bar_full[s], ph);
+            if constexpr (W8) {
+                const int as = kb % kAStages;
+                const uint32_t aph = (kb / kAStages) & 1;
+                mbar_wait(&bar_a_full[as], aph);
+                tc_fence_after();
+                if (tma::elect_one_sync()) {
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ++ks) {
                         const uint32_t a_t = tmem + A_COL + as * 64 + ks * 8;
@@ -151,8 +158,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                     }
                     tc_commit(&bar_a_empty[as]);
                     tc_commit(&bar_x_empty[s]);
-                } else {
-                    tc_fence_after();
+                    if (kb == num_kb - 1) tc_commit(&bar_d_full);
+                }
+            } else {
+                tc_fence_after();
+                if (tma::elect_one_sync()) {
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ++ks) {
                         const uint32_t wa = st_addr + ks * 32;
@@ -161,9 +171,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                     }
                     tc_commit(&bar_w_empty[s]);
                     tc_commit(&bar_x_empty[s]);
+                    if (kb == num_kb - 1) tc_commit(&bar_d_full);
                 }
             }
-            tc_commit(&bar_d_full);   // (with num_kb == 0 nothing was issued: the commit completes at once)
+            __syncwarp();
+        }
+        if (num_kb == 0) {
+            if (tma::elect_one_sync()) tc_commit(&bar_d_full);   // nothing was issued: the commit completes at once
+            __syncwarp();
         }
     } else {
         // ================= converter warps (u8 -> fp16 -> TMEM), then epilogue =================
@@ -177,14 +192,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 const int as = kb % kAStages;
                 const uint32_t aph = (kb / kAStages) & 1;
                 mbar_wait(&bar_full[s], ph);
-                const uint8_t* wt = smem + (size_t)s * STAGE_BYTES + row * 128;
+                const uint32_t wt = smem_u32(smem + (size_t)s * STAGE_BYTES + row * 128);
                 uint4 v[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int chunk = (hf * 4 + c) ^ (row & 7);      // SWIZZLE_128B: 16-byte chunk index XOR row % 8
-                    v[c] = *reinterpret_cast<const uint4*>(wt + chunk * 16);
+                    v[c] = tma::lds_128(wt + chunk * 16);
                 }
-                mbar_arrive(&bar_w_empty[s]);                        // the u8 tile is in registers now
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_w_empty[s]);         // every lane of this warp has issued its reads of the u8 tile
                 uint32_t r[32];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -198,7 +214,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 tmem_st_x32(tmem + ((uint32_t)(q * 32) << 16) + A_COL + as * 64 + hf * 32, r);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
-                mbar_arrive(&bar_a_full[as]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_a_full[as]);
             }
         }
         // ---- epilogue: this warp owns accumulator rows [32q, 32q+32) and token columns [hf*NT/2, (hf+1)*NT/2)

@@ -15,6 +15,28 @@ namespace tma {
 constexpr long long kSpinLimit = 1ll << 22;   // bounded waits: a pipeline bug traps instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// One lane of a fully converged warp (elect.sync).  Single-thread instructions that take UNIFORM operands (tcgen05.mma,
+// tcgen05.commit, cp.async.bulk.tensor) must be issued under this predicate from warp-uniform control flow: behind a plain
+// `if (lane == 0)` the compiler cannot prove the operands uniform and wraps every such instruction in a per-lane "waterfall" loop
+// (R2UR + ELECT + BRA.U.ANY) -- measured 122 cycles per tcgen05.mma issue instead of ~10 (tools/umma_probe.cu, profiles/).
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// 128-bit shared-memory load through the shared window (a generic `*ptr` compiles to LD.E.128 when the compiler cannot prove the
+// address space -- longer latency than LDS.128)
+__device__ __forceinline__ uint4 lds_128(uint32_t smem_addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr));
+    return v;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -28,20 +50,24 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    for (long long spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (spin > kSpinLimit) __trap();
-    }
+    if (mbar_try_wait(addr, parity)) return;          // the common case in a running pipeline: no loop bookkeeping at all
+    for (int spin = 0; !mbar_try_wait(addr, parity); ++spin)
+        if (spin > (1 << 22)) __trap();               // bounded: a pipeline bug traps instead of hanging the GPU
 }
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
 // one box of the tensor map -> shared memory; c0 = element column, c1 = row

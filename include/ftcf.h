@@ -43,7 +43,8 @@ int ftcf_device_check(void);
 /* Kernels (and NCCL collectives) launched by this library in this process so far. */
 long long ftcf_launch_count(void);
 /* Process-wide tuning knobs (defaults are the tuned values): "pdl" 0/1 programmatic dependent launch,
- * "skinny_target_ctas" CTAs per skinny-GEMM launch, "skinny_prefetch_rows" rows each CTA prefetches into L2 up front. */
+ * "skinny_target_ctas" / "decode_target_ctas" CTAs per streaming / tcgen05 decode-GEMM launch, "decode_impl" 3 (tcgen05) or 1
+ * (streaming mma.sync kernel) for the INT8 decode GEMMs, "mmha_bulk" 0/1, ... (the full list is in csrc/capi.cu). */
 int ftcf_set_tunable(const char* name, int value);
 
 /* Debug: per-CTA timeline of the decode kernels.  Between start and stop every instrumented kernel appends one 56-byte record
@@ -52,6 +53,11 @@ int ftcf_set_tunable(const char* name, int value);
  * tools/trace_step.py turns it into a per-launch timeline of one decode step. */
 int ftcf_debug_trace_start(unsigned capacity);
 int ftcf_debug_trace_stop(void* out_host, unsigned max_records, unsigned* n);
+/* Debug: device buffer of 64 x 8 int64 (or NULL to remove) that CTA (0,0,0) of every decode-GEMM launch fills with per-K-step
+ * clock stamps: converter warp [0] before / [1] after the wait for the weight stage, [2] after the conversion, [3] after the
+ * wait for a free TMEM stage, [4] after tcgen05.st; MMA warp [5] before / [6] after its wait for the TMEM stage, [7] after
+ * issuing the MMAs and commits (tools/decode_gemm_probe.py). */
+int ftcf_debug_decode_probe(void* dev_buf);
 
 /* ------------------------------------------------------------------------------------------------
  * Weight-only INT8 quantiser (CPU).  Replaces ft::symmetric_quantize<half,half|float> +
@@ -82,15 +88,16 @@ int ftcf_int8_ampere_to_b200_host(const int8_t* processed_ampere, size_t k, size
  * impl: 0 = auto, 1 = force the skinny (m <= 32 streaming) kernel, 2 = force the tcgen05 kernel. */
 int ftcf_gemm_w8a16(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n,
                     int k, int act, int impl, void* stream);
-/* Same, with a hint naming the weight matrix the NEXT GEMM on this stream will read (K-major, n rows of row_bytes):
- * the streaming kernel queues L2 prefetches for the head of that matrix behind its own last loads, so HBM does not
- * idle across the kernel boundary.  The hint is optional (NULL) and never changes results. */
+/* Same, with a launch hint (optional, NULL = defaults; never changes results):
+ *   target_ctas  CTAs the launch should aim for (0: automatic).  The decode layer runs its two branches side by side and gives
+ *                each GEMM a share of the GPU's CTA slots, so that neither branch queues behind the other;
+ *   no_pdl       1: launch without the programmatic-dependent-launch attribute (the kernel then starts after its predecessor
+ *                has finished instead of parking its CTAs on the SMs while it waits). */
 typedef struct {
-    const void* w;
-    int32_t n, row_bytes;
-} ftcf_prefetch_hint;
+    int32_t target_ctas, no_pdl;
+} ftcf_launch_hint;
 int ftcf_gemm_w8a16_ex(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n,
-                       int k, int act, int impl, const ftcf_prefetch_hint* next, void* stream);
+                       int k, int act, int impl, const ftcf_launch_hint* hint, void* stream);
 
 /* y[m,n] = x[m,k] . W, W given K-major as W^T fp16 [n,k]; fp32 accumulate.  out_f32 = 1 writes fp32 (LM head
  * logits, models/gptneox/GptNeoX.cc:869-912), else fp16 with optional bias + tanh-GELU applied with the
@@ -99,7 +106,7 @@ int ftcf_gemm_w8a16_ex(const void* x, const uint8_t* w_nk, const void* scale, co
 int ftcf_gemm_f16(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
                   int out_f32, int impl, void* stream);
 int ftcf_gemm_f16_ex(const void* x, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy, int act,
-                     int out_f32, int impl, const ftcf_prefetch_hint* next, void* stream);
+                     int out_f32, int impl, const ftcf_launch_hint* hint, void* stream);
 
 /* Decode-step variants (m <= 4 rows) with the layer's glue fused in as a prologue: every CTA first builds its input
  *   r = ((add_ffn + add_attn) + add_bias) + x     -- the previous layer's parallel-residual add (skipped when add_ffn is NULL)

@@ -446,24 +446,24 @@ def test_fused_prologue_rejects_large_m(lib, cuda):
 
 @pytest.mark.parametrize("m", [1, 7, 8, 20])
 @pytest.mark.parametrize("n,k", [(5120, 20480), (2048, 8192), (5120, 5120), (96, 4096)])
-def test_w8a16_skinny_split_k(lib, cuda, m, n, k):
-    """GEMMs with few row tiles are split along k (partials + last-arriver reduction): same tolerance, deterministic, and the
-    ticket counters reset themselves (the second call must give bit-identical output)."""
+def test_w8a16_launch_hints_do_not_change_results(lib, cuda, m, n, k):
+    """The launch hint of ftcf_gemm_w8a16_ex (CTA target, no-PDL) and the k-split it implies on the tcgen05 decode kernel never
+    change the result beyond the summation order (same tolerance), and every choice is deterministic."""
     torch.manual_seed(99 + m + n)
     w = (torch.randn(k, n, device=cuda) * 0.002).half()
     p, s, q = _quant(w)
     x = torch.randn(m, k, device=cuda).half()
     bias = (0.05 * torch.randn(n, device=cuda)).half()
-    capi.check(lib.ftcf_set_tunable(b"skinny_ksplit", 1))
-    capi.check(lib.ftcf_set_tunable(b"skinny_target_ctas", 444))
-    try:
-        y1 = _gemm_w8(lib, x, p, s, bias, m, n, k, 1, impl=1)
-        y2 = _gemm_w8(lib, x, p, s, bias, m, n, k, 1, impl=1)
-    finally:
-        capi.check(lib.ftcf_set_tunable(b"skinny_ksplit", 0))
-        capi.check(lib.ftcf_set_tunable(b"skinny_target_ctas", 0))
-    assert torch.equal(y1, y2)
     ref = R.gelu_f32((x.float() @ (q.float() * s.float()[None, :])).cpu() + bias.float().cpu())
-    assert_close(f"split-k w8a16 m={m} n={n} k={k}", y1.float().cpu(), ref, rtol=2e-3, atol=3e-3)
-    y0 = _gemm_w8(lib, x, p, s, bias, m, n, k, 1, impl=1)
-    assert_close("split vs unsplit", y1.float().cpu(), y0.float().cpu(), rtol=2e-3, atol=2e-3)
+    for impl in (0, 1, 3):
+        for target, no_pdl in ((0, 0), (148, 1), (444, 0)):
+            hint = capi.LaunchHint(target, no_pdl)
+            ys = []
+            for _ in range(2):
+                y = torch.empty(m, n, dtype=torch.float16, device=cuda)
+                capi.check(lib.ftcf_gemm_w8a16_ex(x.data_ptr(), p.data_ptr(), s.data_ptr(), bias.data_ptr(), y.data_ptr(), m, n, k, 1, impl, hint,
+                                                  stream()))
+                torch.cuda.synchronize()
+                ys.append(y)
+            assert torch.equal(ys[0], ys[1])
+            assert_close(f"w8a16 impl={impl} target={target} m={m} n={n} k={k}", ys[0].float().cpu(), ref, rtol=2e-3, atol=3e-3)

@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--m", type=int, nargs="+", default=[1])
 ap.add_argument("--layers", type=int, default=40)
 ap.add_argument("--impl", type=int, default=1)
+ap.add_argument("--tun", type=str, default="", help="extra tunables name=value,... applied to every tcgen05 run")
 a = ap.parse_args()
 lib = capi.load()
 dev = torch.device("cuda:0")
@@ -54,8 +55,11 @@ def run(m, reps=10):
 
 for m in a.m:
     if a.impl == 3:
-        for pdl in (1, 0):
-            for ctas, min_kb in ((296, 8), (148, 8), (240, 8), (296, 4), (444, 8), (296, 16)):
+        for item in filter(None, a.tun.split(",")):
+            k_, _, v_ = item.partition("=")
+            capi.check(lib.ftcf_set_tunable(k_.encode(), int(v_)))
+        for pdl in (1,):
+            for ctas, min_kb in ((296, 8), (148, 8), (160, 40), (240, 8), (296, 4)):
                 lib.ftcf_set_tunable(b"pdl", pdl)
                 lib.ftcf_set_tunable(b"decode_target_ctas", ctas)
                 lib.ftcf_set_tunable(b"decode_min_kb", min_kb)
