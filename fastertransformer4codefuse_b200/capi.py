@@ -44,7 +44,7 @@ class SamplingParams(C.Structure):
 
 
 class LaunchHint(C.Structure):
-    _fields_ = [("target_ctas", C.c_int32), ("no_pdl", C.c_int32)]
+    _fields_ = [("target_ctas", C.c_int32), ("no_pdl", C.c_int32), ("stages", C.c_int32)]
 
 
 class TpExchange(C.Structure):

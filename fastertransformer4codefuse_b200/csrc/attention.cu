@@ -702,18 +702,70 @@ __global__ void __launch_bounds__(MMHA_THREADS, 6) mmha_decode_bulk_kernel(const
         return;
     }
     __threadfence();
+    // merge of the nact partials (fixed order): the per-split weights exp(m_s - M) go to shared memory once, then every thread
+    // sums its dimension with independent loads, four in flight (the naive loop chained ~3 * nact dependent L2 round trips)
     const float* all = p.partial + (size_t)(b * H + h) * p.splits * (DH + 2);
+    float* s_w = s_sc;                        // nact <= grid.z weights; s_sc holds CH floats, larger merges fall back to s_out
+    float* s_l = &s_out[0][0];
+    const bool fits = nact <= CH;
     float M = -INFINITY;
-    for (int s2 = 0; s2 < nact; ++s2) M = fmaxf(M, __ldcg(&all[s2 * (DH + 2) + DH]));
-    for (int d = tid; d < DH; d += MMHA_THREADS) {
-        float L = 0.f, O = 0.f;
+    for (int s2 = tid; s2 < nact; s2 += MMHA_THREADS) M = fmaxf(M, __ldcg(&all[s2 * (DH + 2) + DH]));
+    M = block_max(M, s_red);
+    float Lp = 0.f;
+    for (int s2 = tid; s2 < nact; s2 += MMHA_THREADS) {
+        const float mi = __ldcg(&all[s2 * (DH + 2) + DH]);
+        const float wgt = (mi == -INFINITY) ? 0.f : __expf(mi - M);
+        if (fits) s_w[s2] = wgt;
+        Lp = fmaf(__ldcg(&all[s2 * (DH + 2) + DH + 1]), wgt, Lp);
+    }
+    (void)s_l;
+    // the normaliser is summed in split order by one thread so that it does not depend on the reduction tree
+    __syncthreads();
+    float L = 0.f;
+    if (fits) {
+        for (int s2 = 0; s2 < nact; ++s2) L = fmaf(__ldcg(&all[s2 * (DH + 2) + DH + 1]), s_w[s2], L);
+    } else {
         for (int s2 = 0; s2 < nact; ++s2) {
             const float mi = __ldcg(&all[s2 * (DH + 2) + DH]);
-            const float wgt = (mi == -INFINITY) ? 0.f : __expf(mi - M);
-            L = fmaf(__ldcg(&all[s2 * (DH + 2) + DH + 1]), wgt, L);
-            O = fmaf(__ldcg(&all[s2 * (DH + 2) + d]), wgt, O);
+            L = fmaf(__ldcg(&all[s2 * (DH + 2) + DH + 1]), (mi == -INFINITY) ? 0.f : __expf(mi - M), L);
         }
-        ctx[d] = __float2half_rn(O * (1.f / (L + 1e-6f)));
+    }
+    for (int d = tid; d < DH; d += MMHA_THREADS) {
+        float O0 = 0.f, O1 = 0.f, O2 = 0.f, O3 = 0.f;
+        int s2 = 0;
+        if (fits) {
+            for (; s2 + 8 <= nact; s2 += 8) {        // eight partial rows requested before the first is used
+                float a[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = __ldcg(&all[(s2 + u) * (DH + 2) + d]);
+#pragma unroll
+                for (int u = 0; u < 8; u += 4) {
+                    O0 = fmaf(a[u], s_w[s2 + u], O0);
+                    O1 = fmaf(a[u + 1], s_w[s2 + u + 1], O1);
+                    O2 = fmaf(a[u + 2], s_w[s2 + u + 2], O2);
+                    O3 = fmaf(a[u + 3], s_w[s2 + u + 3], O3);
+                }
+            }
+            for (; s2 + 4 <= nact; s2 += 4) {
+                const float a0 = __ldcg(&all[(s2 + 0) * (DH + 2) + d]), a1 = __ldcg(&all[(s2 + 1) * (DH + 2) + d]);
+                const float a2 = __ldcg(&all[(s2 + 2) * (DH + 2) + d]), a3 = __ldcg(&all[(s2 + 3) * (DH + 2) + d]);
+                O0 = fmaf(a0, s_w[s2], O0);
+                O1 = fmaf(a1, s_w[s2 + 1], O1);
+                O2 = fmaf(a2, s_w[s2 + 2], O2);
+                O3 = fmaf(a3, s_w[s2 + 3], O3);
+            }
+        }
+        for (; s2 < nact; ++s2) {
+            float wgt;
+            if (fits) {
+                wgt = s_w[s2];
+            } else {
+                const float mi = __ldcg(&all[s2 * (DH + 2) + DH]);
+                wgt = (mi == -INFINITY) ? 0.f : __expf(mi - M);
+            }
+            O0 = fmaf(__ldcg(&all[s2 * (DH + 2) + d]), wgt, O0);
+        }
+        ctx[d] = __float2half_rn(((O0 + O1) + (O2 + O3)) * (1.f / (L + 1e-6f)));
     }
     if (tid == 0) {
         p.counters[b * H + h] = 0;

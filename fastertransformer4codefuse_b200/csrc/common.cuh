@@ -68,7 +68,7 @@ __device__ __forceinline__ unsigned long long trc_now(bool who = true)
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ void trc_emit(int kind, unsigned long long t0, unsigned long long t1, unsigned long long t2, int a, int b)
+__device__ __forceinline__ void trc_emit(int kind, unsigned long long t0, unsigned long long t1, unsigned long long t2, int a, int b, int extra = 0)
 {
     if (g_trc_buf == nullptr) return;
     const unsigned i = atomicAdd(g_trc_cnt, 1u);
@@ -78,7 +78,7 @@ __device__ __forceinline__ void trc_emit(int kind, unsigned long long t0, unsign
     r.kind = kind;
     r.cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     r.ncta = gridDim.x * gridDim.y * gridDim.z;
-    r.a = a; r.b = b; r.pad = 0;
+    r.a = a; r.b = b; r.pad = extra;
     g_trc_buf[i] = r;
 }
 #define FTCF_TRACE_INSTALLER(name)                                                        \

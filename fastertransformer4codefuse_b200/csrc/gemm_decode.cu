@@ -33,7 +33,7 @@ std::atomic<int> g_dg_target_ctas{296};   // tunable "decode_target_ctas": CTAs 
 std::atomic<int> g_dg_min_kb{8};          // tunable "decode_min_kb": fewest 128-byte K steps a k-split may get
 std::atomic<int> g_dg_evict_first{1};     // tunable "decode_evict_first"
 std::atomic<int> g_dg_fake_tiled{0};      // EXPERIMENT (timing only, wrong results): weight stages fetched as contiguous 16 KB runs
-std::atomic<int> g_dg_max_stages{6};      // tunable "decode_max_stages": cap on the weight-ring depth (16 KB per stage)
+std::atomic<int> g_dg_max_stages{4};      // tunable "decode_max_stages": cap on the weight-ring depth (16 KB per stage)
 
 // ---- split-K scratch: one (partials, tickets) slot per STREAM.  Launches on one stream are ordered (a PDL-launched successor
 // touches its scratch only after griddepcontrol.wait), so one slot per stream is enough, and engines / threads that use
@@ -102,7 +102,7 @@ constexpr int kTileM = 128;            // output features per CTA (UMMA M)
 constexpr int kAStages = 3;            // TMEM A-operand stages, 64 columns each
 constexpr uint32_t kTmemCols = 256;    // two CTAs per SM share the 512 columns
 constexpr uint32_t D_COL = 0, A_COL = 64;
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 10;
 constexpr uint32_t W_BYTES = kTileM * 128;   // one weight box: 128 features x 128 k (u8)
 constexpr int BK = 128;
 
@@ -288,9 +288,13 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             // ---- zero the activation slabs once (rows >= m stay zero for the whole launch)
             for (int i = ct; i < (int)(kAStages * X_BYTES / 16); i += 256) reinterpret_cast<uint4*>(slab0)[i] = make_uint4(0, 0, 0, 0);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tensor core reads these rows through the async proxy
+            constexpr int PU = 3;                // vectors per thread per batch: 256 threads x 3 x 8 = 6144 columns in one go
             pdl_wait();                         // x / add_ffn / add_attn come from the previous kernels
             trc_t1 = trc_now(trc_who);
-            // ---- fused residual + LayerNorm into xs (same arithmetic as ftcf_add_bias_attn_ffn_residual + ftcf_layernorm)
+            // ---- fused residual + LayerNorm into xs (same arithmetic as ftcf_add_bias_attn_ffn_residual + ftcf_layernorm).
+            // A thread owns up to PU 16-byte vectors of the row and issues ALL their loads before it touches any of them (one L2
+            // round trip per pass instead of one per vector: the prologue is on the critical path of every layer -- 4.6 us before,
+            // profiles/r2m_timeline_a.txt).
             const SkPro& pro = args.pro;
             const int k = args.k, pitch = k + 8, nvec = k >> 3;
             const bool writer = pro.x_out != nullptr && blockIdx.x == 0 && blockIdx.z == 0;
@@ -305,35 +309,49 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             }
             for (int b = 0; b < args.m; ++b) {
                 float sum = 0.f, sq = 0.f;
-                for (int vi = ct; vi < nvec; vi += 256) {
-                    uint4 v = *reinterpret_cast<const uint4*>(pro.x + (size_t)b * k + vi * 8);
-                    if (gather) {
-                        v = tp_gather_vec(pro.tpx, tp_slot, b, vi, v, pro.add_bias);
-                        if (writer) *reinterpret_cast<uint4*>(pro.x_out + (size_t)b * k + vi * 8) = v;
-                    } else if (pro.add_ffn != nullptr) {
-                        const uint4 fv = *reinterpret_cast<const uint4*>(pro.add_ffn + (size_t)b * k + vi * 8);
-                        const uint4 av = *reinterpret_cast<const uint4*>(pro.add_attn + (size_t)b * k + vi * 8);
-                        uint4 bv = make_uint4(0, 0, 0, 0);
-                        if (pro.add_bias != nullptr) bv = *reinterpret_cast<const uint4*>(pro.add_bias + vi * 8);
-                        __half2* xh = reinterpret_cast<__half2*>(&v);
-                        const __half2* fh = reinterpret_cast<const __half2*>(&fv);
-                        const __half2* ah = reinterpret_cast<const __half2*>(&av);
-                        const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+                for (int base = ct; base < nvec; base += 256 * PU) {
+                    uint4 v[PU], fv[PU], av[PU], bv[PU];
+#pragma unroll
+                    for (int u = 0; u < PU; ++u) {
+                        const int vi = base + u * 256;
+                        v[u] = fv[u] = av[u] = bv[u] = make_uint4(0, 0, 0, 0);
+                        if (vi < nvec) {
+                            v[u] = *reinterpret_cast<const uint4*>(pro.x + (size_t)b * k + vi * 8);
+                            if (!gather && pro.add_ffn != nullptr) {
+                                fv[u] = *reinterpret_cast<const uint4*>(pro.add_ffn + (size_t)b * k + vi * 8);
+                                av[u] = *reinterpret_cast<const uint4*>(pro.add_attn + (size_t)b * k + vi * 8);
+                                if (pro.add_bias != nullptr) bv[u] = ld_ro_16(pro.add_bias + vi * 8);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < PU; ++u) {
+                        const int vi = base + u * 256;
+                        if (vi >= nvec) continue;
+                        if (gather) {
+                            v[u] = tp_gather_vec(pro.tpx, tp_slot, b, vi, v[u], pro.add_bias);
+                            if (writer) *reinterpret_cast<uint4*>(pro.x_out + (size_t)b * k + vi * 8) = v[u];
+                        } else if (pro.add_ffn != nullptr) {
+                            __half2* xh = reinterpret_cast<__half2*>(&v[u]);
+                            const __half2* fh = reinterpret_cast<const __half2*>(&fv[u]);
+                            const __half2* ah = reinterpret_cast<const __half2*>(&av[u]);
+                            const __half2* bh = reinterpret_cast<const __half2*>(&bv[u]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                __half2 r = __hadd2(fh[j], ah[j]);
+                                if (pro.add_bias != nullptr) r = __hadd2(r, bh[j]);
+                                xh[j] = __hadd2(r, xh[j]);
+                            }
+                            if (writer) *reinterpret_cast<uint4*>(pro.x_out + (size_t)b * k + vi * 8) = v[u];
+                        }
+                        *reinterpret_cast<uint4*>(xs + (size_t)b * pitch + vi * 8) = v[u];
+                        const __half2* vh = reinterpret_cast<const __half2*>(&v[u]);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            __half2 r = __hadd2(fh[j], ah[j]);
-                            if (pro.add_bias != nullptr) r = __hadd2(r, bh[j]);
-                            xh[j] = __hadd2(r, xh[j]);
+                            const float2 f = __half22float2(vh[j]);
+                            sum += f.x + f.y;
+                            sq += f.x * f.x + f.y * f.y;
                         }
-                        if (writer) *reinterpret_cast<uint4*>(pro.x_out + (size_t)b * k + vi * 8) = v;
-                    }
-                    *reinterpret_cast<uint4*>(xs + (size_t)b * pitch + vi * 8) = v;
-                    const __half2* vh = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = __half22float2(vh[j]);
-                        sum += f.x + f.y;
-                        sq += f.x * f.x + f.y * f.y;
                     }
                 }
                 sum = warp_sum(sum);
@@ -352,20 +370,34 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                 const float mean = ts / k;
                 const float rstd = rsqrtf(tss / k - mean * mean + pro.eps);
                 const __half2 mean_h = __float2half2_rn(mean), rstd_h = __float2half2_rn(rstd);
-                for (int vi = ct; vi < nvec; vi += 256) {
-                    uint4 v = *reinterpret_cast<uint4*>(xs + (size_t)b * pitch + vi * 8);
-                    const uint4 gq = ld_ro_16(pro.gamma + vi * 8);
-                    const uint4 bq = ld_ro_16(pro.beta + vi * 8);
-                    const __half2* gh = reinterpret_cast<const __half2*>(&gq);
-                    const __half2* bh = reinterpret_cast<const __half2*>(&bq);
-                    __half2* vh = reinterpret_cast<__half2*>(&v);
+                for (int base = ct; base < nvec; base += 256 * PU) {
+                    uint4 gq[PU], bq[PU];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) vh[j] = __hfma2(__hmul2_rn(__hsub2_rn(vh[j], mean_h), rstd_h), gh[j], bh[j]);
-                    *reinterpret_cast<uint4*>(xs + (size_t)b * pitch + vi * 8) = v;
+                    for (int u = 0; u < PU; ++u) {
+                        const int vi = base + u * 256;
+                        gq[u] = bq[u] = make_uint4(0, 0, 0, 0);
+                        if (vi < nvec) {
+                            gq[u] = ld_ro_16(pro.gamma + vi * 8);
+                            bq[u] = ld_ro_16(pro.beta + vi * 8);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < PU; ++u) {
+                        const int vi = base + u * 256;
+                        if (vi >= nvec) continue;
+                        uint4 v = *reinterpret_cast<uint4*>(xs + (size_t)b * pitch + vi * 8);
+                        const __half2* gh = reinterpret_cast<const __half2*>(&gq[u]);
+                        const __half2* bh = reinterpret_cast<const __half2*>(&bq[u]);
+                        __half2* vh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) vh[j] = __hfma2(__hmul2_rn(__hsub2_rn(vh[j], mean_h), rstd_h), gh[j], bh[j]);
+                        *reinterpret_cast<uint4*>(xs + (size_t)b * pitch + vi * 8) = v;
+                    }
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
+        const unsigned long long trc_pro = trc_now(trc_who);     // end of the fused prologue (== trc_t1 without one)
         int s = 0, as = 0;
         uint32_t ph = 0, aph = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -495,7 +527,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             }
         }
         tc_fence_before();
-        if (trc_who) trc_emit(TRC_GEMM_W8, trc_t0, trc_t1, trc_t2, args.n, args.k);
+        if (trc_who) trc_emit(TRC_GEMM_W8, trc_t0, trc_t1, trc_t2, args.n, args.k, (int)(trc_pro - trc_t1));
     }
     __syncthreads();
     if (warp == 1) {
@@ -583,9 +615,12 @@ int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, con
         per_stage += x_bytes;
     }
     int fit = fixed < budget ? (int)((budget - fixed) / per_stage) : 0;
-    if (fit < 3) fit = (int)((220 * 1024 - fixed) / per_stage);      // the prologue rows crowd the ring out: one CTA per SM then
+    const int want_stages = hint != nullptr ? hint->stages : 0;
+    if (fit < 3 || want_stages > fit) fit = (int)((220 * 1024 - fixed) / per_stage);      // one CTA per SM: the prologue rows crowd the
+                                                                                          // ring out, or the caller asked for a deeper ring
     FTCF_REQUIRE(fit >= 2, FTCF_ERR_UNSUPPORTED, "decode gemm: m=%d k=%d does not fit shared memory", m, k);
-    const int cap = std::min(dg::kMaxStages, std::max(2, g_dg_max_stages.load(std::memory_order_relaxed)));
+    int cap = std::min(dg::kMaxStages, std::max(2, g_dg_max_stages.load(std::memory_order_relaxed)));
+    if (want_stages > 0) cap = std::min(dg::kMaxStages, std::max(2, want_stages));
     const int stages = std::min(std::min(fit, cap), std::max(kb_per, 2));
     a.stages = stages;
     const size_t smem = fixed + (size_t)stages * per_stage;

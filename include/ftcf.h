@@ -92,9 +92,12 @@ int ftcf_gemm_w8a16(const void* x, const uint8_t* w_nk, const void* scale, const
  *   target_ctas  CTAs the launch should aim for (0: automatic).  The decode layer runs its two branches side by side and gives
  *                each GEMM a share of the GPU's CTA slots, so that neither branch queues behind the other;
  *   no_pdl       1: launch without the programmatic-dependent-launch attribute (the kernel then starts after its predecessor
- *                has finished instead of parking its CTAs on the SMs while it waits). */
+ *                has finished instead of parking its CTAs on the SMs while it waits);
+ *   stages       see below. */
 typedef struct {
     int32_t target_ctas, no_pdl;
+    int32_t stages;   /* tcgen05 decode GEMM: depth of the 16 KB weight ring (0: automatic = as deep as lets two CTAs share an SM;
+                         deeper rings take the SM for one CTA -- for a GEMM that runs beside small kernels, not beside another GEMM) */
 } ftcf_launch_hint;
 int ftcf_gemm_w8a16_ex(const void* x, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m, int n,
                        int k, int act, int impl, const ftcf_launch_hint* hint, void* stream);

@@ -456,8 +456,8 @@ def test_w8a16_launch_hints_do_not_change_results(lib, cuda, m, n, k):
     bias = (0.05 * torch.randn(n, device=cuda)).half()
     ref = R.gelu_f32((x.float() @ (q.float() * s.float()[None, :])).cpu() + bias.float().cpu())
     for impl in (0, 1, 3):
-        for target, no_pdl in ((0, 0), (148, 1), (444, 0)):
-            hint = capi.LaunchHint(target, no_pdl)
+        for target, no_pdl, stages in ((0, 0, 0), (148, 1, 8), (444, 0, 3)):
+            hint = capi.LaunchHint(target, no_pdl, stages)
             ys = []
             for _ in range(2):
                 y = torch.empty(m, n, dtype=torch.float16, device=cuda)

@@ -70,18 +70,20 @@ for g in launches:
                      last_start=(rr["t0"].max() - T0) / 1e3, wait_end=(rr["t1"].min() - T0) / 1e3,
                      first_data=(rr["t2"][rr["t2"] > 0].min() - T0) / 1e3 if (rr["t2"] > 0).any() else float("nan"),
                      first_end=(rr["t3"].min() - T0) / 1e3, end=(rr["t3"].max() - T0) / 1e3,
-                     mb=(k[1] * k[2] * (1 if k[0] == 1 else 2) / 1e6) if k[0] in (1, 2) else 0.0))
+                     mb=(k[1] * k[2] * (1 if k[0] == 1 else 2) / 1e6) if k[0] in (1, 2) else 0.0,
+                     pro=float(np.median(rr["pad"])) / 1e3, cta_med=float(np.median(rr["t3"].astype(np.int64) - rr["t0"].astype(np.int64))) / 1e3,
+                     data_med=float(np.median((rr["t2"].astype(np.int64) - rr["t1"].astype(np.int64))[rr["t2"] > 0])) / 1e3 if (rr["t2"] > 0).any() else float("nan")))
 rows.sort(key=lambda d: d["first"])
 per_layer = max(1, (len(rows) - 4) // max(a.layers, 1))
 print(f"{len(rows)} launches in the step (~{per_layer} per layer)")
-print(f"{'kernel':9s} {'n':>6s} {'k':>6s} {'CTAs':>5s} | {'start':>8s} {'lastCTA':>8s} {'deps ok':>8s} {'1st data':>8s} {'1st end':>8s} {'end':>8s} | {'dur':>6s} {'GB/s':>7s}")
+print(f"{'kernel':9s} {'n':>6s} {'k':>6s} {'CTAs':>5s} | {'start':>8s} {'lastCTA':>8s} {'deps ok':>8s} {'1st data':>8s} {'1st end':>8s} {'end':>8s} | {'dur':>6s} {'GB/s':>7s} | {'prolog':>6s} {'->data':>6s} {'CTA us':>6s}  (medians per CTA)")
 mid = len(rows) // 2
 sel = rows[:per_layer + 2] + rows[mid - (mid % per_layer if per_layer else 0):][:per_layer * a.show] + rows[-4:]
 for d in sel:
     dur = d["end"] - d["wait_end"] if d["name"].startswith("gemm") else d["end"] - d["first"]
     gbs = d["mb"] / dur * 1e3 / 1e3 if d["mb"] and dur > 0 else 0
     print(f"{d['name']:9s} {d['n']:6d} {d['k']:6d} {d['ncta']:5d} | {d['first']:8.1f} {d['last_start']:8.1f} {d['wait_end']:8.1f} {d['first_data']:8.1f} "
-          f"{d['first_end']:8.1f} {d['end']:8.1f} | {dur:6.1f} {gbs * 1e3:7.0f}")
+          f"{d['first_end']:8.1f} {d['end']:8.1f} | {dur:6.1f} {gbs * 1e3:7.0f} | {d['pro']:6.1f} {d['data_med']:6.1f} {d['cta_med']:6.1f}")
 # aggregate per kernel type
 agg = {}
 for d in rows:
