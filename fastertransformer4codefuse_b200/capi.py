@@ -48,7 +48,7 @@ class LaunchHint(C.Structure):
 
 
 class TpExchange(C.Structure):
-    _fields_ = [("peer_data", C.c_void_p * 8), ("peer_counter", C.c_void_p * 8), ("tp", C.c_int32), ("rank", C.c_int32),
+    _fields_ = [("peer_data", C.c_void_p * 8), ("tp", C.c_int32), ("rank", C.c_int32),
                 ("m_max", C.c_int32), ("h", C.c_int32), ("step", C.c_void_p), ("step_base", C.c_int32), ("layer_num", C.c_int32)]
 
 
@@ -119,7 +119,7 @@ SIGNATURES = {
     "ftcf_gemm_f16_ln": (C.c_int, [C.POINTER(LnPrologue), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_void_p]),
     "ftcf_gemm_w8a16_tp_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TpExchange), C.c_int, C.c_int, C.c_int, C.c_int,
-                                          C.c_int, C.c_void_p]),
+                                          C.c_int, C.POINTER(LaunchHint), C.c_void_p]),
     "ftcf_tp_gather_residual": (C.c_int, [C.POINTER(TpExchange), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ftcf_transpose_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ftcf_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),

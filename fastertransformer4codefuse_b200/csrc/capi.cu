@@ -43,7 +43,7 @@ int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, con
                       const SkPro* pro, cudaStream_t st, const ftcf_tp_exchange* push = nullptr, int push_kind = 0, int push_layer = 0,
                       const ftcf_launch_hint* hint = nullptr);
 bool gemm_decode_supported(int m, int n, int k);
-extern std::atomic<int> g_dg_target_ctas, g_dg_min_kb, g_dg_evict_first, g_dg_max_stages, g_dg_fake_tiled;
+extern std::atomic<int> g_dg_target_ctas, g_dg_min_kb, g_dg_evict_first, g_dg_max_stages, g_dg_fake_tiled, g_dg_cluster;
 std::atomic<int> g_decode_impl{3};   // tunable "decode_impl": 3 = tcgen05 decode GEMM for int8 at m <= 32 (default), 1 = round-1 streaming mma.sync kernel
 extern std::atomic<int> g_prefill_mma, g_mmha_onepass, g_mmha_splits, g_mmha_bulk;
 extern std::atomic<int> g_mmha_pdl, g_mmha_prefetch, g_sk_carveout, g_sk_evict_first, g_tc_ksplit, g_sk_target_ctas;
@@ -78,6 +78,7 @@ extern "C" int ftcf_set_tunable(const char* name, int value)
     else if (n == "decode_impl") g_decode_impl.store(value);
     else if (n == "decode_max_stages") g_dg_max_stages.store(value);
     else if (n == "decode_fake_tiled") g_dg_fake_tiled.store(value);
+    else if (n == "decode_cluster") g_dg_cluster.store(value);
     else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_tunable: unknown tunable %s", name);
     return FTCF_OK;
 }
@@ -204,10 +205,10 @@ extern "C" int ftcf_gemm_w8a16_ln(const ftcf_ln_prologue* pro, const uint8_t* w_
 }
 
 extern "C" int ftcf_gemm_w8a16_tp_push(const void* x, const uint8_t* w_nk, const void* scale, const ftcf_tp_exchange* ex, int kind, int layer,
-                                       int m, int n, int k, void* stream)
+                                       int m, int n, int k, const ftcf_launch_hint* hint, void* stream)
 {
     FTCF_REQUIRE(x && w_nk && scale && ex, FTCF_ERR_INVALID, "gemm_w8a16_tp_push: null operand");
-    return gemm_w8a16_decode(x, w_nk, scale, nullptr, nullptr, m, n, k, 0, nullptr, as_stream(stream), ex, kind, layer);
+    return gemm_w8a16_decode(x, w_nk, scale, nullptr, nullptr, m, n, k, 0, nullptr, as_stream(stream), ex, kind, layer, hint);
 }
 
 extern "C" int ftcf_gemm_f16_ln(const ftcf_ln_prologue* pro, const void* w_nk, const void* bias, void* y, int m, int n, int k, int ldy,

@@ -225,47 +225,44 @@ __device__ __forceinline__ uint32_t f2_to_h2(float a, float b)
 }
 
 // ---------------------------------------------------------------- tensor-parallel exchange (ftcf_tp_exchange, include/ftcf.h)
-__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_release_sys_add_u32(unsigned* p, unsigned v)
-{
-    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 struct TpIndex {
     int slot;
-    unsigned uses;
+    unsigned epoch;
 };
 __device__ __forceinline__ TpIndex tp_index(const ftcf_tp_exchange& ex, int layer)
 {
     const int g = (*ex.step - ex.step_base) * ex.layer_num + layer;
     return {g & 1, (unsigned)(g >> 1) + 1u};
 }
-__device__ __forceinline__ size_t tp_data_offset(const ftcf_tp_exchange& ex, int slot, int kind, int src)
+// offset, in 8-byte flagged words, of row 0 of (slot, kind, source rank)
+__device__ __forceinline__ size_t tp_word_offset(const ftcf_tp_exchange& ex, int slot, int kind, int src)
 {
-    return ((size_t)(slot * 2 + kind) * ex.tp + src) * ex.m_max * ex.h;      // in fp16 elements
+    return ((size_t)(slot * 2 + kind) * ex.tp + src) * ex.m_max * (size_t)(ex.h >> 1);
 }
-__device__ __forceinline__ int tp_counter_index(int slot, int kind) { return (slot * 2 + kind) * 32; }   // uint32 units, 128 bytes apart
-// Gather side, one thread: block until both kinds of this rank's (slot) counters show `uses` complete exchanges.  Bounded: a
-// peer that died traps this kernel instead of hanging the GPU for good.
-__device__ __forceinline__ void tp_wait_counters(const ftcf_tp_exchange& ex, const TpIndex ix)
+// push side: one flagged word {fp16 pair, epoch}, a single 8-byte store (data and flag become visible together)
+__device__ __forceinline__ void tp_store_word(void* area, size_t word, uint32_t pair, unsigned epoch)
 {
-    const unsigned want = ix.uses * (unsigned)ex.tp * (unsigned)((ex.h + 127) / 128);
-    const unsigned* c = ex.peer_counter[ex.rank];
-    for (int kind = 0; kind < 2; ++kind) {
-        const unsigned* p = c + tp_counter_index(ix.slot, kind);
-        for (long long spin = 0; ld_acquire_sys_u32(p) < want; ++spin)
-            if (spin > (1ll << 28)) __trap();
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(static_cast<uint2*>(area) + word), "r"(pair), "r"(epoch) : "memory");
+}
+// gather side: the four flagged words of 8 consecutive columns, polled until all carry `epoch`.  Bounded: a peer that died traps
+// this kernel instead of hanging the GPU for good.
+__device__ __forceinline__ uint4 tp_load_vec(const void* area, size_t word0, unsigned epoch)
+{
+    const uint4* p = reinterpret_cast<const uint4*>(static_cast<const uint2*>(area) + word0);
+    uint4 a, b;
+    for (long long spin = 0;; ++spin) {
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p) : "memory");
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p + 1) : "memory");
+        if (a.y == epoch && a.w == epoch && b.y == epoch && b.w == epoch) break;
+        if (spin > (1ll << 26)) __trap();
     }
+    return make_uint4(a.x, a.z, b.x, b.z);
 }
 // 8 consecutive elements of row b of the all-reduced residual:  sum_r [((ffn_r + attn_r) + bias) + half(x / tp)]  in fp32, rounded
 // once.  Same fp16 adds per rank as residual_kernel<0> (kernels/add_residual_kernels.cu:116-176).
-__device__ __forceinline__ uint4 tp_gather_vec(const ftcf_tp_exchange& ex, int slot, int b, int vi, uint4 xv, const __half* bias)
+__device__ __forceinline__ uint4 tp_gather_vec(const ftcf_tp_exchange& ex, const TpIndex ix, int b, int vi, uint4 xv, const __half* bias)
 {
-    const __half* data = static_cast<const __half*>(ex.peer_data[ex.rank]);
+    const void* area = ex.peer_data[ex.rank];
     const float inv_tp = 1.f / ex.tp;
     __half2 xs[4];
     const __half2* xh = reinterpret_cast<const __half2*>(&xv);
@@ -278,9 +275,10 @@ __device__ __forceinline__ uint4 tp_gather_vec(const ftcf_tp_exchange& ex, int s
         xs[j] = __floats2half2_rn(f.x * inv_tp, f.y * inv_tp);
     }
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const size_t row_words = (size_t)b * (ex.h >> 1) + (size_t)vi * 4;
     for (int r = 0; r < ex.tp; ++r) {
-        const uint4 fv = __ldcg(reinterpret_cast<const uint4*>(data + tp_data_offset(ex, slot, 1, r) + (size_t)b * ex.h + vi * 8));
-        const uint4 av = __ldcg(reinterpret_cast<const uint4*>(data + tp_data_offset(ex, slot, 0, r) + (size_t)b * ex.h + vi * 8));
+        const uint4 fv = tp_load_vec(area, tp_word_offset(ex, ix.slot, 1, r) + row_words, ix.epoch);
+        const uint4 av = tp_load_vec(area, tp_word_offset(ex, ix.slot, 0, r) + row_words, ix.epoch);
         const __half2* fh = reinterpret_cast<const __half2*>(&fv);
         const __half2* ah = reinterpret_cast<const __half2*>(&av);
 #pragma unroll

@@ -180,7 +180,7 @@ struct ftcf_gptneox {
     static constexpr int kTpMaxRows = 32;
 
     // options
-    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_kv_prefetch = 0, opt_pro_ctas = 148, opt_tp_fused = 1;
+    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_kv_prefetch = 0, opt_pro_ctas = 148, opt_tp_fused = 1, opt_tp_gather_kernel = -1;
     // CTA targets of the four decode GEMMs of a layer in the fused path (0: pro_ctas for QKV / FFN1, the kernel's default for O / FFN2)
     int opt_qkv_ctas = 0, opt_ffn1_ctas = 0, opt_o_ctas = 0, opt_ffn2_ctas = 160,   // FFN2 at one CTA per SM leaves the attention kernel its slots (profiles/r2_decode_experiments.txt)
          opt_ffn2_no_pdl = 0, opt_ffn2_stages = 0, opt_o_stages = 0, opt_ffn2_after_attn = 0, opt_qkv_first = 0;
@@ -251,8 +251,8 @@ int tp_exchange_setup(ftcf_gptneox* e)
     const int t = e->t;
     if (t <= 1 || t > 8 || e->cfg.int8_mode != 1 || e->h % 128 != 0) return FTCF_OK;
     cudaStream_t st = e->stream;
-    e->tp_data_bytes = (size_t)2 * 2 * t * ftcf_gptneox::kTpMaxRows * e->h * sizeof(__half);
-    const size_t area_bytes = e->tp_data_bytes + 4 * 128;
+    e->tp_data_bytes = (size_t)2 * 2 * t * ftcf_gptneox::kTpMaxRows * (e->h / 2) * 8;   // 8-byte flagged words, two columns each
+    const size_t area_bytes = e->tp_data_bytes;
     int ok = 1;
     cudaIpcMemHandle_t mine{};
     if (cudaMalloc(&e->tp_area, area_bytes) != cudaSuccess || cudaMemset(e->tp_area, 0, area_bytes) != cudaSuccess ||
@@ -292,10 +292,7 @@ int tp_exchange_setup(ftcf_gptneox* e)
     if (e->tp_fused) {
         ftcf_tp_exchange& x = e->tpx;
         x = ftcf_tp_exchange{};
-        for (int r = 0; r < t; ++r) {
-            x.peer_data[r] = base[r];
-            x.peer_counter[r] = reinterpret_cast<uint32_t*>(static_cast<char*>(base[r]) + e->tp_data_bytes);
-        }
+        for (int r = 0; r < t; ++r) x.peer_data[r] = base[r];
         x.tp = t; x.rank = e->rank; x.m_max = ftcf_gptneox::kTpMaxRows; x.h = e->h; x.layer_num = e->cfg.layer_num;
     }
     return FTCF_OK;
@@ -346,7 +343,7 @@ int run_layer(ftcf_gptneox* e, int l, int m, AttnFn&& attn_fn, bool tp_decode = 
         // decode rows with the exchange area up: the O / FFN2 epilogues store their tiles into every rank's area and
         // ftcf_tp_gather_residual rebuilds the all-reduced residual (no residual kernel, no ncclAllReduce)
         const bool tp_push = tp_decode && e->tp_fused && e->opt_tp_fused != 0 && c.int8_mode == 1 && m <= ftcf_gptneox::kTpMaxRows;
-        if (tp_push) FTCF_TRY(ftcf_gemm_w8a16_tp_push(e->inter.p, static_cast<const uint8_t*>(L.w[3]), L.scale[3], &e->tpx, 1, l, m, e->h, e->inter_l, sb));
+        if (tp_push) FTCF_TRY(ftcf_gemm_w8a16_tp_push(e->inter.p, static_cast<const uint8_t*>(L.w[3]), L.scale[3], &e->tpx, 1, l, m, e->h, e->inter_l, nullptr, sb));
         else FTCF_TRY(engine_gemm(e, sb, e->inter.p, l, 3, nullptr, e->ffn.p, m, e->h, e->inter_l, 0));
         if (fork) FTCF_CUDA_CHECK(cudaEventRecord(e->ev_join, sb));
         if (ln_pro) {
@@ -356,7 +353,7 @@ int run_layer(ftcf_gptneox* e, int l, int m, AttnFn&& attn_fn, bool tp_decode = 
             FTCF_TRY(engine_gemm(e, st, e->n1.p, l, 0, nullptr, e->qkv.p, m, 3 * e->hl, e->h, 0));
         }
         FTCF_TRY(attn_fn(l));
-        if (tp_push) FTCF_TRY(ftcf_gemm_w8a16_tp_push(e->ctx.p, static_cast<const uint8_t*>(L.w[1]), L.scale[1], &e->tpx, 0, l, m, e->h, e->hl, st));
+        if (tp_push) FTCF_TRY(ftcf_gemm_w8a16_tp_push(e->ctx.p, static_cast<const uint8_t*>(L.w[1]), L.scale[1], &e->tpx, 0, l, m, e->h, e->hl, nullptr, st));
         else FTCF_TRY(engine_gemm(e, st, e->ctx.p, l, 1, nullptr, e->attn.p, m, e->h, e->hl, 0));
         if (fork) FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join, 0));
         // ffn2_b slot holds the summed (o + ffn2) bias, already divided by t (huggingface_convert.py:35-41,192-206)
@@ -575,6 +572,7 @@ extern "C" int ftcf_gptneox_set_option(ftcf_gptneox* e, const char* name, int va
     else if (n == "kv_prefetch") e->opt_kv_prefetch = value;
     else if (n == "pro_ctas") e->opt_pro_ctas = value;
     else if (n == "tp_fused") e->opt_tp_fused = value;
+    else if (n == "tp_gather_kernel") e->opt_tp_gather_kernel = value;
     else if (n == "qkv_ctas") e->opt_qkv_ctas = value;
     else if (n == "ffn1_ctas") e->opt_ffn1_ctas = value;
     else if (n == "o_ctas") e->opt_o_ctas = value;
@@ -621,6 +619,11 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
         __half* ffn[2] = {e->ffn.as<__half>(), e->ffn_b.as<__half>()};
         const int L = run_layers ? c.layer_num : 0;
         const bool w8 = c.int8_mode == 1;
+        const bool tp_fused = e->t > 1;          // fused_on with t > 1 implies the exchange area is up (see ftcf_gptneox_forward)
+        // Who sums the exchanged partials: at t = 2 every QKV / FFN1 CTA gathers its own copy in its prologue (2 x 2 x 20 KB from
+        // L2); from t = 4 that would be hundreds of CTAs x 160+ KB per layer, so one small kernel gathers once and the prologues
+        // only normalise.
+        const bool tp_gather_kernel = tp_fused && (e->opt_tp_gather_kernel >= 0 ? e->opt_tp_gather_kernel != 0 : e->t > 2);
         if (run_layers) {
             const size_t total = (size_t)B * e->h / 8;
             embedding_prev_token_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xb[0], e->wte, s.out_ids, s.step, B, e->h, c.vocab_size);
@@ -638,9 +641,21 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
                 pro.x = xb[0];
             } else {
                 pro.x = xb[(l - 1) & 1];
-                pro.add_ffn = ffn[(l - 1) & 1];
-                pro.add_attn = attn[(l - 1) & 1];
                 pro.add_bias = e->layers[l - 1].ffn2_b;   // (b_o + b_ffn2) / t, huggingface_convert.py:35-41,192-206
+                if (tp_gather_kernel) {
+                    pro.x = xb[l & 1];                    // already all-reduced by ftcf_tp_gather_residual below
+                    pro.add_bias = nullptr;
+                    return pro;
+                }
+                if (tp_fused) {
+                    // tensor parallel: the partial sums of EVERY rank's O / FFN2 of layer l - 1 sit in this rank's exchange area
+                    // (pushed by their epilogues over NVLink); the prologue sums them -- the all-reduce of GptNeoXDecoder.cc:348-359
+                    pro.tp_exchange = &e->tpx;
+                    pro.tp_layer = l - 1;
+                } else {
+                    pro.add_ffn = ffn[(l - 1) & 1];
+                    pro.add_attn = attn[(l - 1) & 1];
+                }
                 if (store) pro.x_out = xb[l & 1];
             }
             return pro;
@@ -648,6 +663,8 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
         for (int l = 0; l < L; ++l) {
             const LayerW& lw = e->layers[l];
             cudaStream_t sb = e->opt_two_branch ? e->side : st;
+            if (tp_gather_kernel && l > 0)
+                FTCF_TRY(ftcf_tp_gather_residual(&e->tpx, l - 1, xb[(l - 1) & 1], e->layers[l - 1].ffn2_b, xb[l & 1], B, st));
             // The FFN branch is issued first: measured best (its two big weight streams take the SMs, the attention branch's
             // shorter kernels fill in).  Issuing QKV first, or forking only after QKV, was 8-25 % slower per token.
             if (e->opt_two_branch) {
@@ -680,6 +697,7 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
                 return ftcf_gemm_f16_ln(&p2, lw.w[2], lw.ffn1_b, e->inter.p, B, e->inter_l, e->h, e->inter_l, 1, 0, sb);
             };
             auto ffn2 = [&]() -> int {
+                if (tp_fused) return ftcf_gemm_w8a16_tp_push(e->inter.p, static_cast<const uint8_t*>(lw.w[3]), lw.scale[3], &e->tpx, 1, l, B, e->h, e->inter_l, &h2, sb);
                 if (w8) return ftcf_gemm_w8a16_ex(e->inter.p, static_cast<const uint8_t*>(lw.w[3]), lw.scale[3], nullptr, ffn[l & 1], B, e->h, e->inter_l, 0, e->opt_gemm_impl, &h2, sb);
                 return ftcf_gemm_f16(e->inter.p, lw.w[3], nullptr, ffn[l & 1], B, e->h, e->inter_l, e->h, 0, 0, 1, sb);
             };
@@ -688,6 +706,7 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
                 return ftcf_gemm_f16_ln(&p1, lw.w[0], nullptr, e->qkv.p, B, 3 * e->hl, e->h, 3 * e->hl, 0, 0, st);
             };
             auto oproj = [&]() -> int {
+                if (tp_fused) return ftcf_gemm_w8a16_tp_push(e->ctx.p, static_cast<const uint8_t*>(lw.w[1]), lw.scale[1], &e->tpx, 0, l, B, e->h, e->hl, &ho, st);
                 if (w8) return ftcf_gemm_w8a16_ex(e->ctx.p, static_cast<const uint8_t*>(lw.w[1]), lw.scale[1], nullptr, attn[l & 1], B, e->h, e->hl, 0, e->opt_gemm_impl, &ho, st);
                 return ftcf_gemm_f16(e->ctx.p, lw.w[1], nullptr, attn[l & 1], B, e->h, e->hl, e->h, 0, 0, 1, st);
             };
@@ -724,11 +743,14 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
             if (e->opt_two_branch) FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join, 0));
             if (kvpf) FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join2, 0));
         }
-        // final LayerNorm (on the last layer's residual sum) as the prologue of the LM head
-        const ftcf_ln_prologue pf = prologue(L, e->lnf_g, e->lnf_b, false);
-        return ftcf_gemm_f16_ln(&pf, e->lm_head, nullptr, e->logits.p, B, e->Vp, e->h, e->Vp, 0, 1, st);
-    }
-    if (run_layers) {
+        if (!tp_fused) {
+            // final LayerNorm (on the last layer's residual sum) as the prologue of the LM head
+            const ftcf_ln_prologue pf = prologue(L, e->lnf_g, e->lnf_b, false);
+            return ftcf_gemm_f16_ln(&pf, e->lm_head, nullptr, e->logits.p, B, e->Vp, e->h, e->Vp, 0, 1, st);
+        }
+        // tensor parallel: the last layer's exchange is gathered into e->x, then the sharded LM head below
+        if (L > 0) FTCF_TRY(ftcf_tp_gather_residual(&e->tpx, L - 1, xb[(L - 1) & 1], e->layers[L - 1].ffn2_b, e->x.p, B, st));
+    } else if (run_layers) {
         const size_t total = (size_t)B * e->h / 8;
         embedding_prev_token_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->x.as<__half>(), e->wte, s.out_ids, s.step, B, e->h,
                                                                                       c.vocab_size);
@@ -852,7 +874,8 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     FTCF_TRY(e->samp_ws.ensure(ws_bytes));
     const int splits = ftcf_mmha_choose_splits(B, e->Hl, max_len);
     FTCF_TRY(e->mmha_part.ensure((size_t)B * e->Hl * splits * (dh + 2) * 4 + 256));
-    e->fused_on = e->opt_fused_ln == 1 && B <= 4 && e->t == 1 && c.use_gptj_residual != 0 && e->h % 128 == 0 && e->h <= 16384;
+    e->fused_on = e->opt_fused_ln == 1 && B <= 4 && c.use_gptj_residual != 0 && e->h % 128 == 0 && e->h <= 16384 &&
+                  (e->t == 1 || (e->tp_fused && e->opt_tp_fused != 0 && c.int8_mode == 1));
     if (e->fused_on) {
         FTCF_TRY(e->attn_b.ensure((size_t)B * e->h * 2));
         FTCF_TRY(e->ffn_b.ensure((size_t)B * e->h * 2));
@@ -944,10 +967,11 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     memset(e->host_hist, 0, (size_t)max_len * sizeof(int32_t));   // the previous request has drained (forward ends with a sync)
 
     if (e->tp_fused) {
-        // exchange counters restart with the request (every rank's earlier pushes were consumed before its previous request
-        // returned).  A peer's first push of THIS request follows its prefill, whose all-reduces need this rank's, which follow
-        // this memset in stream order; without a prefill a one-int all-reduce provides the same ordering.
-        FTCF_CUDA_CHECK(cudaMemsetAsync(static_cast<char*>(e->tp_area) + e->tp_data_bytes, 0, 4 * 128, st));
+        // the exchange epochs restart with the request, so the area is zeroed (every rank's earlier pushes were consumed before its
+        // previous request returned).  A peer's first push of THIS request follows its prefill, whose all-reduces need this
+        // rank's, which follow this memset in stream order; without a prefill a one-int all-reduce provides the same ordering.
+        const size_t used = (size_t)2 * 2 * e->t * e->tpx.m_max * (e->h / 2) * 8;
+        FTCF_CUDA_CHECK(cudaMemsetAsync(e->tp_area, 0, used, st));
         if (!has_prefill) FTCF_NCCL_CHECK(g_nccl.AllReduce(s.counters, s.counters, 1, /*ncclInt32*/ 2, NCCL_SUM, e->comm, st));
         e->tpx.step = s.step;
         e->tpx.step_base = has_prefill ? S + 1 : S;      // the first loop iteration that runs the layers

@@ -32,6 +32,7 @@ namespace ftcf {
 std::atomic<int> g_dg_target_ctas{296};   // tunable "decode_target_ctas": CTAs a launch aims for (k-splits fill up to it)
 std::atomic<int> g_dg_min_kb{8};          // tunable "decode_min_kb": fewest 128-byte K steps a k-split may get
 std::atomic<int> g_dg_evict_first{1};     // tunable "decode_evict_first"
+std::atomic<int> g_dg_cluster{1};         // tunable "decode_cluster": k-splits of a tile as a thread-block cluster (DSMEM reduction)
 std::atomic<int> g_dg_fake_tiled{0};      // EXPERIMENT (timing only, wrong results): weight stages fetched as contiguous 16 KB runs
 std::atomic<int> g_dg_max_stages{4};      // tunable "decode_max_stages": cap on the weight-ring depth (16 KB per stage)
 
@@ -120,7 +121,29 @@ struct Args {
     SkPro pro;        // PRO only
     ftcf_tp_exchange push;   // push.tp > 1: the epilogue stores the output into every rank's exchange area instead of y
     int push_kind, push_layer;
+    int cluster;      // 1: the gridDim.z k-splits of a tile form a thread-block cluster and reduce through distributed shared
+                      // memory (the leader's `red` buffer at red_off) instead of global partials + ticket
+    uint32_t red_off; // byte offset of the reduction buffer [(S-1)][m][128] fp32 inside the aligned dynamic shared memory
 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// fp32 store into the shared memory of CTA `rank` of this cluster (same offset as `local_addr` in this CTA's window)
+__device__ __forceinline__ void st_cluster_f32(uint32_t local_addr, uint32_t rank, float v)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
 
 // PRO = false: activations arrive by TMA (map_x: [m, k] fp16, box NT rows x 128 bytes, rows >= m read as zero)
 // PRO = true : activations are built in shared memory by the fused residual + LayerNorm prologue (m <= 4)
@@ -204,6 +227,13 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
     long long* const probe = (blockIdx.x == 0 && blockIdx.z == 0) ? g_probe : nullptr;
+    // converter / epilogue geometry (warps 2..9): TMEM lane quarter, half of the K step / of the token columns, feature row
+    const int q = warp & 3, hf = (warp - 2) >> 2, row = q * 32 + lane, ct = threadIdx.x - 64;
+    const int col = n0 + row;
+    const bool col_ok = col < args.n;
+    bool finish = true;                         // this CTA runs the second half of the epilogue for its tile
+    unsigned long long trc_t0 = 0, trc_t1 = 0, trc_t2 = 0;
+    int trc_pro_ns = 0;
 
     if (warp == 0) {
         // ================= TMA producer (whole warp in lock step, one elected lane issues) =================
@@ -277,13 +307,9 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         }
     } else {
         // ================= converter warps (u8 -> fp16 -> TMEM), then epilogue =================
-        const int q = warp & 3;                 // TMEM lane quarter this warp may touch
-        const int hf = (warp - 2) >> 2;         // which half of the K step (convert) / of the token columns (epilogue)
-        const int row = q * 32 + lane;          // feature row inside the tile == TMEM lane
-        const int ct = threadIdx.x - 64;        // 0..255 among the converter threads
         const bool trc_who = ct == 0;
-        const unsigned long long trc_t0 = trc_now(trc_who);
-        unsigned long long trc_t1 = trc_t0, trc_t2 = 0;
+        trc_t0 = trc_now(trc_who);
+        trc_t1 = trc_t0;
         if constexpr (PRO) {
             // ---- zero the activation slabs once (rows >= m stay zero for the whole launch)
             for (int i = ct; i < (int)(kAStages * X_BYTES / 16); i += 256) reinterpret_cast<uint4*>(slab0)[i] = make_uint4(0, 0, 0, 0);
@@ -299,14 +325,10 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             const int k = args.k, pitch = k + 8, nvec = k >> 3;
             const bool writer = pro.x_out != nullptr && blockIdx.x == 0 && blockIdx.z == 0;
             const bool gather = pro.tpx.tp > 1;
-            int tp_slot = 0;
-            if (gather) {
-                // tensor-parallel gather: the previous layer's O / FFN2 tiles of every rank arrive in this rank's exchange area
-                const TpIndex ix = tp_index(pro.tpx, pro.tp_layer);
-                tp_slot = ix.slot;
-                if (ct == 0) tp_wait_counters(pro.tpx, ix);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
+            // tensor-parallel gather: the previous layer's O / FFN2 tiles of every rank arrive in this rank's exchange area as
+            // flagged words; tp_gather_vec polls exactly the words it needs
+            TpIndex tpix{0, 0};
+            if (gather) tpix = tp_index(pro.tpx, pro.tp_layer);
             for (int b = 0; b < args.m; ++b) {
                 float sum = 0.f, sq = 0.f;
                 for (int base = ct; base < nvec; base += 256 * PU) {
@@ -329,7 +351,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                         const int vi = base + u * 256;
                         if (vi >= nvec) continue;
                         if (gather) {
-                            v[u] = tp_gather_vec(pro.tpx, tp_slot, b, vi, v[u], pro.add_bias);
+                            v[u] = tp_gather_vec(pro.tpx, tpix, b, vi, v[u], pro.add_bias);
                             if (writer) *reinterpret_cast<uint4*>(pro.x_out + (size_t)b * k + vi * 8) = v[u];
                         } else if (pro.add_ffn != nullptr) {
                             __half2* xh = reinterpret_cast<__half2*>(&v[u]);
@@ -397,7 +419,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
-        const unsigned long long trc_pro = trc_now(trc_who);     // end of the fused prologue (== trc_t1 without one)
+        trc_pro_ns = (int)(trc_now(trc_who) - trc_t1);           // duration of the fused prologue (0 without one)
         int s = 0, as = 0;
         uint32_t ph = 0, aph = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -447,25 +469,32 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             if (++s == stages) { s = 0; ph ^= 1; }
             if (++as == kAStages) { as = 0; aph ^= 1; }
         }
-        // ---- epilogue: this warp owns accumulator rows [32q, 32q+32) and token columns [hf*NT/2, (hf+1)*NT/2)
+        // ---- epilogue, first half: wait for the accumulators; k-splits publish their partial sums
         if constexpr (!PRO) pdl_wait();          // y may still be read by the previous kernel
         mbar_wait(&bar_d_full, 0);
         tc_fence_after();
-        const int col = n0 + row;
-        const bool col_ok = col < args.n;
-        float sc = 1.f, bs = 0.f;
-        if (col_ok) sc = __half2float(args.scale[col]);
-        if (args.bias != nullptr && col_ok) bs = __half2float(args.bias[col]);
-        const bool push_on = args.push.tp > 1;
-        size_t push_off = 0;
-        int push_cnt = 0;
-        if (push_on) {
-            const TpIndex ix = tp_index(args.push, args.push_layer);
-            push_off = tp_data_offset(args.push, ix.slot, args.push_kind, args.push.rank);
-            push_cnt = tp_counter_index(ix.slot, args.push_kind);
-        }
-        bool finish = true;
-        if (S > 1) {
+        if (S > 1 && args.cluster) {
+            // thread-block cluster of the S k-splits of this tile: ranks 1..S-1 store their accumulators into the leader's
+            // shared memory (distributed shared memory), one cluster barrier, the leader adds them in rank order
+            const uint32_t crank = cluster_ctarank();
+            finish = crank == 0;
+            if (crank != 0) {
+                const uint32_t red_local = smem_u32(smem + args.red_off);
+#pragma unroll
+                for (int c0 = 0; c0 < NT / 2; c0 += 8) {
+                    const int tcol = hf * (NT / 2) + c0;
+                    if (tcol >= args.m) continue;
+                    uint32_t acc[8];
+                    tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + D_COL + tcol, acc);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int tok = tcol + j;
+                        if (tok < args.m)
+                            st_cluster_f32(red_local + (uint32_t)((((crank - 1) * args.m + tok) * kTileM + row) * 4), 0, __uint_as_float(acc[j]));
+                    }
+                }
+            }
+        } else if (S > 1) {
             // publish this k-split's partial accumulators, take a ticket; only the last arriver of the tile goes on
 #pragma unroll
             for (int c0 = 0; c0 < NT / 2; c0 += 8) {
@@ -490,44 +519,66 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             finish = s_last != 0;
             if (finish) __threadfence();
         }
-        if (finish) {
+    }
+    if (S > 1 && args.cluster) cluster_sync_all();          // every thread of every CTA of the cluster
+    if (warp >= 2 && finish) {
+        // ---- epilogue, second half (one CTA per tile): scale, bias, activation, store -- or push to every rank
+        const bool clustered = S > 1 && args.cluster;
+        const float* red = reinterpret_cast<const float*>(smem + args.red_off);
+        float sc = 1.f, bs = 0.f;
+        if (col_ok) sc = __half2float(args.scale[col]);
+        if (args.bias != nullptr && col_ok) bs = __half2float(args.bias[col]);
+        const bool push_on = args.push.tp > 1;
+        size_t push_word = 0;
+        unsigned push_epoch = 0;
+        if (push_on) {
+            const TpIndex ix = tp_index(args.push, args.push_layer);
+            push_word = tp_word_offset(args.push, ix.slot, args.push_kind, args.push.rank);
+            push_epoch = ix.epoch;
+        }
 #pragma unroll
-            for (int c0 = 0; c0 < NT / 2; c0 += 8) {
-                const int tcol = hf * (NT / 2) + c0;
-                if (tcol >= args.m) continue;
-                uint32_t acc[8];
-                if (S == 1) tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + D_COL + tcol, acc);
+        for (int c0 = 0; c0 < NT / 2; c0 += 8) {
+            const int tcol = hf * (NT / 2) + c0;
+            if (tcol >= args.m) continue;
+            uint32_t acc[8];
+            if (S == 1 || clustered) tmem_ld_x8(tmem + ((uint32_t)(q * 32) << 16) + D_COL + tcol, acc);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int tok = tcol + j;
-                    if (!col_ok || tok >= args.m) continue;
-                    float v;
-                    if (S == 1) {
-                        v = __uint_as_float(acc[j]);
-                    } else {
-                        v = __ldcg(&args.part[(size_t)tok * args.n + col]);
-                        for (int z = 1; z < S; ++z) v += __ldcg(&args.part[((size_t)z * args.m + tok) * args.n + col]);
+            for (int j = 0; j < 8; ++j) {
+                const int tok = tcol + j;
+                if (tok >= args.m) continue;                 // (warp-uniform; col_ok is per lane: the push pairs lanes by shuffle)
+                float v = 0.f;
+                if (col_ok) {
+                if (S == 1) {
+                    v = __uint_as_float(acc[j]);
+                } else if (clustered) {
+                    v = __uint_as_float(acc[j]);
+                    for (int z = 1; z < S; ++z) v += red[((z - 1) * args.m + tok) * kTileM + row];
+                } else {
+                    v = __ldcg(&args.part[(size_t)tok * args.n + col]);
+                    for (int z = 1; z < S; ++z) v += __ldcg(&args.part[((size_t)z * args.m + tok) * args.n + col]);
+                }
+                v = v * sc + bs;
+                if (args.act == 1) v = gelu_tanh_f32(v);
+                }
+                const __half hv = __float2half_rn(v);
+                if (push_on) {
+                    // one-shot exchange: the tile goes straight from the accumulators into every rank's memory over NVLink as
+                    // flagged words {two adjacent columns, epoch} -- one 8-byte store each, no fence, no separate flag
+                    const uint32_t mine = (uint32_t)__half_as_ushort(hv);
+                    const uint32_t other = __shfl_down_sync(0xffffffffu, mine, 1);
+                    if ((lane & 1) == 0 && col_ok) {
+                        const size_t word = push_word + (size_t)tok * (args.push.h >> 1) + (col >> 1);
+                        for (int r = 0; r < args.push.tp; ++r) tp_store_word(args.push.peer_data[r], word, mine | (other << 16), push_epoch);
                     }
-                    v = v * sc + bs;
-                    if (args.act == 1) v = gelu_tanh_f32(v);
-                    const __half hv = __float2half_rn(v);
-                    if (push_on) {
-                        // one-shot exchange: the tile goes straight from the accumulators into every rank's memory over NVLink
-                        for (int r = 0; r < args.push.tp; ++r)
-                            static_cast<__half*>(args.push.peer_data[r])[push_off + (size_t)tok * args.push.h + col] = hv;
-                    } else {
-                        args.y[(size_t)tok * args.ldy + col] = hv;
-                    }
+                } else if (col_ok) {
+                    args.y[(size_t)tok * args.ldy + col] = hv;
                 }
             }
-            if (push_on) {
-                __threadfence_system();
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (ct < args.push.tp) red_release_sys_add_u32(args.push.peer_counter[ct] + push_cnt, 1u);
-            }
         }
+    }
+    if (warp >= 2) {
         tc_fence_before();
-        if (trc_who) trc_emit(TRC_GEMM_W8, trc_t0, trc_t1, trc_t2, args.n, args.k, (int)(trc_pro - trc_t1));
+        if (ct == 0) trc_emit(TRC_GEMM_W8, trc_t0, trc_t1, trc_t2, args.n, args.k, trc_pro_ns);
     }
     __syncthreads();
     if (warp == 1) {
@@ -561,7 +612,28 @@ static int launch_decode(const CUtensorMap& mw, const CUtensorMap& mx, dg::Args 
         FTCF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         configured.store(smem, std::memory_order_relaxed);
     }
-    const cudaError_t err = launch_pdl_if(pdl, kern, grid, dim3(dg::kThreads), smem, st, mw, mx, a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(dg::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    unsigned na = 0;
+    if (pdl && g_pdl_enabled.load(std::memory_order_relaxed)) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (a.cluster) {     // the k-splits of a tile are one thread-block cluster (distributed-shared-memory reduction)
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = grid.z;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, mw, mx, a);
     FTCF_REQUIRE(err == cudaSuccess, FTCF_ERR_CUDA, "decode gemm launch failed: %s", cudaGetErrorString(err));
     FTCF_LAUNCH_CHECK();
     return FTCF_OK;
@@ -579,7 +651,8 @@ int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, con
     if (pro != nullptr && pro->cta_hint > 0) target = pro->cta_hint;
     if (hint != nullptr && hint->target_ctas > 0) target = hint->target_ctas;
     const bool pdl = hint == nullptr || hint->no_pdl == 0;
-    int S = std::max(1, std::min(target / tiles, kb_all / std::max(1, g_dg_min_kb.load(std::memory_order_relaxed))));
+    // (rounded to nearest: 80 tiles against a target of 148 take two splits, not one)
+    int S = std::max(1, std::min((target + tiles / 2) / tiles, kb_all / std::max(1, g_dg_min_kb.load(std::memory_order_relaxed))));
     S = std::min(S, 16);
     dg::Args a{};
     a.scale = static_cast<const __half*>(scale);
@@ -614,6 +687,12 @@ int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, con
     } else {
         per_stage += x_bytes;
     }
+    // k-splits reduce through distributed shared memory when the leader's buffer is small (decode rows); otherwise through
+    // global partials + ticket
+    const size_t red_bytes = (size_t)(S - 1) * m * dg::kTileM * sizeof(float);
+    const bool cluster = S > 1 && S <= 8 && red_bytes <= 16 * 1024 && g_dg_cluster.load(std::memory_order_relaxed) != 0;
+    const size_t before_red = fixed - 1024;             // bytes behind the ring, relative to the 1024-byte aligned base
+    if (cluster) fixed += red_bytes;
     int fit = fixed < budget ? (int)((budget - fixed) / per_stage) : 0;
     const int want_stages = hint != nullptr ? hint->stages : 0;
     if (fit < 3 || want_stages > fit) fit = (int)((220 * 1024 - fixed) / per_stage);      // one CTA per SM: the prologue rows crowd the
@@ -624,6 +703,10 @@ int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, con
     const int stages = std::min(std::min(fit, cap), std::max(kb_per, 2));
     a.stages = stages;
     const size_t smem = fixed + (size_t)stages * per_stage;
+    if (cluster) {
+        a.cluster = 1;
+        a.red_off = (uint32_t)((size_t)stages * per_stage + before_red);
+    }
     CUtensorMap mw, mx;
     int rc = make_tensor_map_2d(&mw, w_nk, n, k, 1, dg::kTileM);
     if (rc != FTCF_OK) return rc;

@@ -142,21 +142,23 @@ embedding_kernel(__half* __restrict__ out, const __half* __restrict__ table, con
     *reinterpret_cast<uint4*>(out + (size_t)row * n + c * 8) = ld_ro_16(table + (size_t)id * n + c * 8);
 }
 
-// Stand-alone gather side of the tensor-parallel exchange (ftcf_tp_exchange): one CTA per row.
+// Stand-alone gather side of the tensor-parallel exchange (ftcf_tp_exchange): grid (column slices, rows).
 __global__ void __launch_bounds__(256)
 tp_gather_residual_kernel(const ftcf_tp_exchange ex, int layer, const __half* __restrict__ x, const __half* __restrict__ bias,
                           __half* __restrict__ x_out)
 {
+    const unsigned long long trc_t0 = trc_now(threadIdx.x == 0);
     pdl_launch_dependents();
     pdl_wait();
+    const unsigned long long trc_t1 = trc_now(threadIdx.x == 0);
     const TpIndex ix = tp_index(ex, layer);
-    if (threadIdx.x == 0) tp_wait_counters(ex, ix);
-    __syncthreads();
-    const int b = blockIdx.x, nvec = ex.h >> 3;
-    for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+    const int b = blockIdx.y, nvec = ex.h >> 3;
+    const int vi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vi < nvec) {
         const uint4 xv = *reinterpret_cast<const uint4*>(x + (size_t)b * ex.h + vi * 8);
-        *reinterpret_cast<uint4*>(x_out + (size_t)b * ex.h + vi * 8) = tp_gather_vec(ex, ix.slot, b, vi, xv, bias);
+        *reinterpret_cast<uint4*>(x_out + (size_t)b * ex.h + vi * 8) = tp_gather_vec(ex, ix, b, vi, xv, bias);
     }
+    if (threadIdx.x == 0) trc_emit(TRC_RESIDUAL, trc_t0, trc_t1, trc_t1, ex.h, 9);
 }
 
 FTCF_TRACE_INSTALLER(trace_install_norm_residual)
@@ -237,7 +239,7 @@ extern "C" int ftcf_tp_gather_residual(const ftcf_tp_exchange* ex, int layer, co
 {
     FTCF_REQUIRE(ex && x && x_out && ex->tp > 1 && ex->tp <= 8 && m >= 1 && m <= ex->m_max && ex->h % 8 == 0 && ex->step, FTCF_ERR_INVALID,
                  "tp_gather_residual: bad argument");
-    const cudaError_t err = launch_pdl(tp_gather_residual_kernel, dim3(m), dim3(256), 0, as_stream(stream), *ex, layer,
+    const cudaError_t err = launch_pdl(tp_gather_residual_kernel, dim3(ceil_div(ex->h >> 3, 64), m), dim3(64), 0, as_stream(stream), *ex, layer,
                                        static_cast<const __half*>(x), static_cast<const __half*>(bias), static_cast<__half*>(x_out));
     FTCF_REQUIRE(err == cudaSuccess, FTCF_ERR_CUDA, "tp_gather_residual launch failed: %s", cudaGetErrorString(err));
     FTCF_LAUNCH_CHECK();

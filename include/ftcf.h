@@ -119,19 +119,18 @@ int ftcf_gemm_f16_ex(const void* x, const void* w_nk, const void* bias, void* y,
  * kernels/layernorm_kernels.cu:158-286), without their two launches on the layer's critical path. */
 /* Tensor-parallel exchange fused into the decode GEMMs: replaces the residual kernel + ncclAllReduce of
  * models/gptneox/GptNeoXDecoder.cc:348-359 (and the one-shot kernel of kernels/custom_ar_kernels.cu:139,202) at decode sizes.
- * Every rank owns an exchange area that all ranks of the node map (CUDA IPC over NVLink):
- *   data     [2 slots][2 kinds: 0 attn, 1 ffn][tp source ranks][m_max][h] fp16
- *   counters [2 slots][2 kinds] uint32, 128 bytes apart, monotonic within a request
- * Push side (O / FFN2 GEMM of rank r): the epilogue stores each output tile into (slot, kind, source r) of EVERY rank's data
- * area -- remote stores from the kernel that computed the tile -- then adds 1 to that rank's counter (release, system scope).
- * Gather side (fused prologue of the next QKV / FFN1 GEMM, or ftcf_tp_gather_residual): waits until its OWN counters reached
- * uses * tp * tiles, rebuilds every rank's partial  o_r = ((ffn_r + attn_r) + bias) + half(x / tp)  with the reference's fp16 adds
- * (kernels/add_residual_kernels.cu:116-176), sums the tp partials in rank order in fp32 and rounds once: the all-reduce.
+ * Every rank owns an exchange area that all ranks of the node map (CUDA IPC over NVLink), made of 8-byte "flagged words":
+ *   area [2 slots][2 kinds: 0 attn, 1 ffn][tp source ranks][m_max][h / 2] x { fp16 pair, uint32 epoch }
+ * Push side (O / FFN2 GEMM of rank r): the epilogue stores each output tile into (slot, kind, source r) of EVERY rank's area --
+ * remote 8-byte stores from the kernel that computed the tile.  Data and flag travel in ONE store, so there is no fence and no
+ * separate flag write on the critical path (a system-scope release after remote stores costs 6-9 us beside a streaming GEMM).
+ * Gather side (fused prologue of the next QKV / FFN1 GEMM, or ftcf_tp_gather_residual): polls the words it needs until their
+ * epoch is the expected one, rebuilds every rank's partial  o_r = ((ffn_r + attn_r) + bias) + half(x / tp)  with the reference's
+ * fp16 adds (kernels/add_residual_kernels.cu:116-176), sums the tp partials in rank order in fp32 and rounds once: the all-reduce.
  * The exchange index g = (*step - step_base) * layer_num + layer is evaluated on the device (one captured graph serves every
- * token): slot = g & 1, uses = g / 2 + 1. */
+ * token): slot = g & 1, epoch = g / 2 + 1.  The area is zeroed at the start of a request (epoch 0 never matches). */
 typedef struct {
-    void* peer_data[8];            /* data area of every rank, own rank included (device pointers valid in this process) */
-    uint32_t* peer_counter[8];     /* counter area of every rank */
+    void* peer_data[8];            /* exchange area of every rank, own rank included (device pointers valid in this process) */
     int32_t tp, rank, m_max, h;
     const int32_t* step;           /* device scalar: the decode loop's step */
     int32_t step_base, layer_num;
@@ -154,7 +153,7 @@ int ftcf_gemm_f16_ln(const ftcf_ln_prologue* pro, const void* w_nk, const void* 
 /* INT8 GEMM whose epilogue pushes the [m, n = h] output into every rank's exchange area (kind 0: O GEMM, 1: FFN2 GEMM) instead
  * of writing y.  m <= ex->m_max, n == ex->h, k a multiple of 128. */
 int ftcf_gemm_w8a16_tp_push(const void* x, const uint8_t* w_nk, const void* scale, const ftcf_tp_exchange* ex, int kind, int layer,
-                            int m, int n, int k, void* stream);
+                            int m, int n, int k, const ftcf_launch_hint* hint, void* stream);
 /* Stand-alone gather side: x_out[m,h] = all-reduced residual of exchange `layer` (see ftcf_tp_exchange); x is that layer's input. */
 int ftcf_tp_gather_residual(const ftcf_tp_exchange* ex, int layer, const void* x, const void* bias, void* x_out, int m, void* stream);
 

@@ -89,8 +89,9 @@ ids = prompts(cfg, lens, 7, 3)
 box = [None]
 if rank == 0:
     free = oracle_from_rank_weights(cfg, shards, 1).forward(ids, lens, 6)["output_ids"][0, 0, 7:13]
-    cand = [int(t) for i, t in enumerate(free) if i >= 2 and int(t) not in [int(x) for x in free[:i]]]
-    box[0] = cand[0] if cand else None
+    firsts = [(i, int(t)) for i, t in enumerate(free) if int(t) not in [int(x) for x in free[:i]]]   # first occurrence of every token
+    late = [t for i, t in firsts if i >= 2]
+    box[0] = late[0] if late else firsts[-1][1]      # finish after a few tokens if the continuation allows it, else as late as it does
 dist.broadcast_object_list(box, src=0)
 if box[0] is None:
     report("early end_id: no usable token in the free-running continuation (test not exercised)", False)

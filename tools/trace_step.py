@@ -20,15 +20,24 @@ ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--in-len", type=int, default=1024)
 ap.add_argument("--layers", type=int, default=40)
 ap.add_argument("--show", type=int, default=2, help="layers to print launch by launch")
+ap.add_argument("--detail", type=int, default=0, help="1: per-launch distribution of CTA end times and busy times (min 10% 25% 50% 75% 90% max)")
 a = ap.parse_args()
-dev = torch.device("cuda:0")
+# under torchrun (WORLD_SIZE > 1) the model is tensor-parallel and rank 0 prints ITS timeline
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+torch.cuda.set_device(dev)
+comm = None
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+    comm = dist.group.WORLD
 cfg = W.NeoXConfig(head_num=40, size_per_head=128, inter_size=20480, layer_num=a.layers, vocab_size=100864, rotary_embedding_dim=128,
                    start_id=100000, end_id=100863)
-rw = W.make_synthetic_fast(cfg, 1, 0, 1, dev)
+rw = W.make_synthetic_fast(cfg, world, rank, 1, dev)
 rw.w[12 * cfg.layer_num + 3][cfg.end_id].zero_()
 w, q, s = rw.lists()
-op = GptNeoXOp(None, 0, cfg.head_num, cfg.size_per_head, cfg.inter_size, cfg.layer_num, cfg.vocab_size, cfg.rotary_embedding_dim, cfg.start_id,
-               cfg.end_id, 1, 1, 1, 2048, True, w, q, s)
+op = GptNeoXOp(comm, rank, cfg.head_num, cfg.size_per_head, cfg.inter_size, cfg.layer_num, cfg.vocab_size, cfg.rotary_embedding_dim, cfg.start_id,
+               cfg.end_id, world, 1, 1, 2048, True, w, q, s)
 ids = torch.from_numpy(np.random.default_rng(1234).integers(0, cfg.vocab_size - 2, size=(a.batch, a.in_len)).astype(np.int32)).to(dev)
 lens = torch.full((a.batch,), a.in_len, dtype=torch.int32, device=dev)
 op.forward(ids, lens, 12)          # warm-up: captures the graph
@@ -42,6 +51,10 @@ buf = np.zeros(CAP, dtype=rec_t)
 n = C.c_uint(0)
 capi.check(lib.ftcf_debug_trace_stop(buf.ctypes.data, CAP, C.byref(n)))
 r = buf[:n.value]
+if rank != 0:
+    if world > 1:
+        dist.barrier()
+    sys.exit(0)
 print("records:", len(r), op.last_stats)
 ends = np.sort(r[(r["kind"] == 30) & (r["b"] == 3)]["t3"])     # step_finalize of every step
 assert len(ends) >= 4, len(ends)
@@ -73,6 +86,11 @@ for g in launches:
                      mb=(k[1] * k[2] * (1 if k[0] == 1 else 2) / 1e6) if k[0] in (1, 2) else 0.0,
                      pro=float(np.median(rr["pad"])) / 1e3, cta_med=float(np.median(rr["t3"].astype(np.int64) - rr["t0"].astype(np.int64))) / 1e3,
                      data_med=float(np.median((rr["t2"].astype(np.int64) - rr["t1"].astype(np.int64))[rr["t2"] > 0])) / 1e3 if (rr["t2"] > 0).any() else float("nan")))
+    r_ = rows[-1]
+    t3 = np.sort((rr["t3"].astype(np.int64) - int(T0)) / 1e3)
+    dur = np.sort((rr["t3"].astype(np.int64) - np.maximum(rr["t2"], rr["t1"]).astype(np.int64)) / 1e3)
+    pick = lambda a_: " ".join(f"{a_[min(len(a_) - 1, int(qq * (len(a_) - 1)))]:.1f}" for qq in (0, .1, .25, .5, .75, .9, 1))
+    r_["detail"] = f"end deciles [{pick(t3)}]  busy us per CTA [{pick(dur)}]"
 rows.sort(key=lambda d: d["first"])
 per_layer = max(1, (len(rows) - 4) // max(a.layers, 1))
 print(f"{len(rows)} launches in the step (~{per_layer} per layer)")
@@ -84,6 +102,8 @@ for d in sel:
     gbs = d["mb"] / dur * 1e3 / 1e3 if d["mb"] and dur > 0 else 0
     print(f"{d['name']:9s} {d['n']:6d} {d['k']:6d} {d['ncta']:5d} | {d['first']:8.1f} {d['last_start']:8.1f} {d['wait_end']:8.1f} {d['first_data']:8.1f} "
           f"{d['first_end']:8.1f} {d['end']:8.1f} | {dur:6.1f} {gbs * 1e3:7.0f} | {d['pro']:6.1f} {d['data_med']:6.1f} {d['cta_med']:6.1f}")
+    if a.detail:
+        print("          " + d["detail"])
 # aggregate per kernel type
 agg = {}
 for d in rows:
@@ -113,3 +133,5 @@ for t, dlt in ev:
     depth += dlt
     last = t
 print(f"\ntime with NO streaming kernel active (past its dependency wait): {idle:.1f} us of {(hi - lo) / 1e3:.1f} us")
+if world > 1:
+    dist.barrier()
