@@ -54,8 +54,7 @@ class TpExchange(C.Structure):
 
 class LnPrologue(C.Structure):
     _fields_ = [("x", C.c_void_p), ("add_ffn", C.c_void_p), ("add_attn", C.c_void_p), ("add_bias", C.c_void_p),
-                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("x_out", C.c_void_p), ("eps", C.c_float), ("cta_hint", C.c_int32),
-                ("tp_exchange", C.POINTER(TpExchange)), ("tp_layer", C.c_int32)]
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("x_out", C.c_void_p), ("eps", C.c_float), ("cta_hint", C.c_int32)]
 
 
 class GptNeoXConfig(C.Structure):

@@ -190,17 +190,8 @@ extern "C" int ftcf_gemm_w8a16_ln(const ftcf_ln_prologue* pro, const uint8_t* w_
         sp.add_attn = static_cast<const __half*>(pro->add_attn); sp.add_bias = static_cast<const __half*>(pro->add_bias);
         sp.gamma = static_cast<const __half*>(pro->gamma); sp.beta = static_cast<const __half*>(pro->beta);
         sp.x_out = static_cast<__half*>(pro->x_out); sp.eps = pro->eps; sp.cta_hint = pro->cta_hint;
-        if (pro->tp_exchange != nullptr && pro->tp_exchange->tp > 1) {
-            const ftcf_tp_exchange& ex = *pro->tp_exchange;
-            FTCF_REQUIRE(ex.tp <= 8 && ex.rank >= 0 && ex.rank < ex.tp && m <= ex.m_max && k == ex.h && ex.step != nullptr, FTCF_ERR_INVALID,
-                         "gemm_w8a16_ln: bad tensor-parallel gather (tp %d rank %d m %d/%d k %d/%d)", ex.tp, ex.rank, m, ex.m_max, k, ex.h);
-            sp.tpx = ex;
-            sp.tp_layer = pro->tp_layer;
-        }
         return gemm_w8a16_decode(nullptr, w_nk, scale, bias, y, m, n, k, act, &sp, as_stream(stream));
     }
-    FTCF_REQUIRE(pro->tp_exchange == nullptr, FTCF_ERR_UNSUPPORTED, "gemm_w8a16_ln: the tensor-parallel gather needs the tcgen05 decode kernel "
-                 "(m <= 4, k a multiple of 128)");
     return gemm_w8a16_skinny_ln(*pro, w_nk, scale, bias, y, m, n, k, act, as_stream(stream));
 }
 

@@ -131,8 +131,6 @@ struct SkPro {
     __half* x_out;
     float eps;
     int cta_hint;
-    ftcf_tp_exchange tpx;   // tpx.tp > 1: the partials of exchange `tp_layer` stand in for add_ffn / add_attn (tensor-parallel gather)
-    int tp_layer;
 };
 
 
@@ -244,25 +242,21 @@ __device__ __forceinline__ void tp_store_word(void* area, size_t word, uint32_t 
 {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(static_cast<uint2*>(area) + word), "r"(pair), "r"(epoch) : "memory");
 }
-// gather side: the four flagged words of 8 consecutive columns, polled until all carry `epoch`.  Bounded: a peer that died traps
-// this kernel instead of hanging the GPU for good.
-__device__ __forceinline__ uint4 tp_load_vec(const void* area, size_t word0, unsigned epoch)
+// gather side: the flagged words of 8 consecutive columns (4 words = two 16-byte loads) of both kinds from CH source ranks at a
+// time -- all 4 * CH loads are issued before the first flag is looked at, so a gather costs one L2 round trip per CH ranks instead
+// of one per rank and kind -- polled until every word carries `epoch`.  Bounded: a dead peer traps this kernel instead of hanging
+// the GPU for good.
+__device__ __forceinline__ void tp_ld_words(const void* p, uint4& a, uint4& b)
 {
-    const uint4* p = reinterpret_cast<const uint4*>(static_cast<const uint2*>(area) + word0);
-    uint4 a, b;
-    for (long long spin = 0;; ++spin) {
-        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p) : "memory");
-        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p + 1) : "memory");
-        if (a.y == epoch && a.w == epoch && b.y == epoch && b.w == epoch) break;
-        if (spin > (1ll << 26)) __trap();
-    }
-    return make_uint4(a.x, a.z, b.x, b.z);
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(static_cast<const char*>(p) + 16) : "memory");
 }
 // 8 consecutive elements of row b of the all-reduced residual:  sum_r [((ffn_r + attn_r) + bias) + half(x / tp)]  in fp32, rounded
-// once.  Same fp16 adds per rank as residual_kernel<0> (kernels/add_residual_kernels.cu:116-176).
+// once.  Same fp16 adds per rank as residual_kernel<0> (kernels/add_residual_kernels.cu:116-176); ranks are summed in rank order.
+template <int CH>
 __device__ __forceinline__ uint4 tp_gather_vec(const ftcf_tp_exchange& ex, const TpIndex ix, int b, int vi, uint4 xv, const __half* bias)
 {
-    const void* area = ex.peer_data[ex.rank];
+    const uint2* area = static_cast<const uint2*>(ex.peer_data[ex.rank]);
     const float inv_tp = 1.f / ex.tp;
     __half2 xs[4];
     const __half2* xh = reinterpret_cast<const __half2*>(&xv);
@@ -276,19 +270,46 @@ __device__ __forceinline__ uint4 tp_gather_vec(const ftcf_tp_exchange& ex, const
     }
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const size_t row_words = (size_t)b * (ex.h >> 1) + (size_t)vi * 4;
-    for (int r = 0; r < ex.tp; ++r) {
-        const uint4 fv = tp_load_vec(area, tp_word_offset(ex, ix.slot, 1, r) + row_words, ix.epoch);
-        const uint4 av = tp_load_vec(area, tp_word_offset(ex, ix.slot, 0, r) + row_words, ix.epoch);
-        const __half2* fh = reinterpret_cast<const __half2*>(&fv);
-        const __half2* ah = reinterpret_cast<const __half2*>(&av);
+    const size_t kind_words = (size_t)ex.tp * ex.m_max * (size_t)(ex.h >> 1);          // kind 0 -> kind 1 of the same slot
+    const size_t rank_words = (size_t)ex.m_max * (size_t)(ex.h >> 1);
+    const uint2* base = area + tp_word_offset(ex, ix.slot, 0, 0) + row_words;
+    for (int r0 = 0; r0 < ex.tp; r0 += CH) {
+        uint4 w[CH][4];        // [rank][attn lo, attn hi, ffn lo, ffn hi]
+        for (long long spin = 0;; ++spin) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            __half2 o = __hadd2(fh[j], ah[j]);
-            if (bias != nullptr) o = __hadd2(o, bh[j]);
-            o = __hadd2(o, xs[j]);
-            const float2 f = __half22float2(o);
-            acc[2 * j] += f.x;
-            acc[2 * j + 1] += f.y;
+            for (int i = 0; i < CH; ++i) {
+                if (r0 + i < ex.tp) {
+                    const uint2* p = base + (size_t)(r0 + i) * rank_words;
+                    tp_ld_words(p, w[i][0], w[i][1]);
+                    tp_ld_words(p + kind_words, w[i][2], w[i][3]);
+                }
+            }
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                if (r0 + i < ex.tp) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ok = ok && w[i][q].y == ix.epoch && w[i][q].w == ix.epoch;
+                }
+            }
+            if (ok) break;
+            if (spin > (1ll << 24)) __trap();
+        }
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            if (r0 + i < ex.tp) {
+                const uint32_t av[4] = {w[i][0].x, w[i][0].z, w[i][1].x, w[i][1].z};
+                const uint32_t fv[4] = {w[i][2].x, w[i][2].z, w[i][3].x, w[i][3].z};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __half2 o = __hadd2(*reinterpret_cast<const __half2*>(&fv[j]), *reinterpret_cast<const __half2*>(&av[j]));
+                    if (bias != nullptr) o = __hadd2(o, bh[j]);
+                    o = __hadd2(o, xs[j]);
+                    const float2 f = __half22float2(o);
+                    acc[2 * j] += f.x;
+                    acc[2 * j + 1] += f.y;
+                }
+            }
         }
     }
     uint4 out;

@@ -180,7 +180,7 @@ struct ftcf_gptneox {
     static constexpr int kTpMaxRows = 32;
 
     // options
-    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_kv_prefetch = 0, opt_pro_ctas = 148, opt_tp_fused = 1, opt_tp_gather_kernel = -1;
+    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_kv_prefetch = 0, opt_pro_ctas = 148, opt_tp_fused = 1;
     // CTA targets of the four decode GEMMs of a layer in the fused path (0: pro_ctas for QKV / FFN1, the kernel's default for O / FFN2)
     int opt_qkv_ctas = 0, opt_ffn1_ctas = 0, opt_o_ctas = 0, opt_ffn2_ctas = 160,   // FFN2 at one CTA per SM leaves the attention kernel its slots (profiles/r2_decode_experiments.txt)
          opt_ffn2_no_pdl = 0, opt_ffn2_stages = 0, opt_o_stages = 0, opt_ffn2_after_attn = 0, opt_qkv_first = 0;
@@ -572,7 +572,6 @@ extern "C" int ftcf_gptneox_set_option(ftcf_gptneox* e, const char* name, int va
     else if (n == "kv_prefetch") e->opt_kv_prefetch = value;
     else if (n == "pro_ctas") e->opt_pro_ctas = value;
     else if (n == "tp_fused") e->opt_tp_fused = value;
-    else if (n == "tp_gather_kernel") e->opt_tp_gather_kernel = value;
     else if (n == "qkv_ctas") e->opt_qkv_ctas = value;
     else if (n == "ffn1_ctas") e->opt_ffn1_ctas = value;
     else if (n == "o_ctas") e->opt_o_ctas = value;
@@ -620,10 +619,11 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
         const int L = run_layers ? c.layer_num : 0;
         const bool w8 = c.int8_mode == 1;
         const bool tp_fused = e->t > 1;          // fused_on with t > 1 implies the exchange area is up (see ftcf_gptneox_forward)
-        // Who sums the exchanged partials: at t = 2 every QKV / FFN1 CTA gathers its own copy in its prologue (2 x 2 x 20 KB from
-        // L2); from t = 4 that would be hundreds of CTAs x 160+ KB per layer, so one small kernel gathers once and the prologues
-        // only normalise.
-        const bool tp_gather_kernel = tp_fused && (e->opt_tp_gather_kernel >= 0 ? e->opt_tp_gather_kernel != 0 : e->t > 2);
+        // Tensor parallel: the all-reduced residual of layer l - 1 is rebuilt from the exchanged partials by ftcf_tp_gather_residual, a
+        // 10-CTA kernel that heads EACH branch of layer l (the FFN branch keeps its own copy of the residual stream in xs), so both
+        // chains hang off it by programmatic launch.  Measured at tp 2 / 4 (profiles/r2_tp_experiments.txt): gather in every QKV /
+        // FFN1 CTA's prologue 424 / 390 tokens/s, one gather before the fork 369 / 490, one per branch 460 / --.
+        __half* xs[2] = {e->n1.as<__half>(), e->n2.as<__half>()};
         if (run_layers) {
             const size_t total = (size_t)B * e->h / 8;
             embedding_prev_token_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xb[0], e->wte, s.out_ids, s.step, B, e->h, c.vocab_size);
@@ -642,20 +642,15 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
             } else {
                 pro.x = xb[(l - 1) & 1];
                 pro.add_bias = e->layers[l - 1].ffn2_b;   // (b_o + b_ffn2) / t, huggingface_convert.py:35-41,192-206
-                if (tp_gather_kernel) {
-                    pro.x = xb[l & 1];                    // already all-reduced by ftcf_tp_gather_residual below
+                if (tp_fused) {
+                    // the partial sums of EVERY rank's O / FFN2 of layer l - 1 were pushed into this rank's exchange area by their
+                    // epilogues and summed by the branch's gather kernel -- the all-reduce of GptNeoXDecoder.cc:348-359
+                    pro.x = store ? xb[l & 1] : xs[l & 1];
                     pro.add_bias = nullptr;
                     return pro;
                 }
-                if (tp_fused) {
-                    // tensor parallel: the partial sums of EVERY rank's O / FFN2 of layer l - 1 sit in this rank's exchange area
-                    // (pushed by their epilogues over NVLink); the prologue sums them -- the all-reduce of GptNeoXDecoder.cc:348-359
-                    pro.tp_exchange = &e->tpx;
-                    pro.tp_layer = l - 1;
-                } else {
-                    pro.add_ffn = ffn[(l - 1) & 1];
-                    pro.add_attn = attn[(l - 1) & 1];
-                }
+                pro.add_ffn = ffn[(l - 1) & 1];
+                pro.add_attn = attn[(l - 1) & 1];
                 if (store) pro.x_out = xb[l & 1];
             }
             return pro;
@@ -663,8 +658,6 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
         for (int l = 0; l < L; ++l) {
             const LayerW& lw = e->layers[l];
             cudaStream_t sb = e->opt_two_branch ? e->side : st;
-            if (tp_gather_kernel && l > 0)
-                FTCF_TRY(ftcf_tp_gather_residual(&e->tpx, l - 1, xb[(l - 1) & 1], e->layers[l - 1].ffn2_b, xb[l & 1], B, st));
             // The FFN branch is issued first: measured best (its two big weight streams take the SMs, the attention branch's
             // shorter kernels fill in).  Issuing QKV first, or forking only after QKV, was 8-25 % slower per token.
             if (e->opt_two_branch) {
@@ -687,6 +680,11 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
                 FTCF_CUDA_CHECK(cudaStreamWaitEvent(e->side2, e->ev_fork, 0));
                 FTCF_TRY(ftcf_mmha_prefetch_cache(&mp, e->side2));
                 FTCF_CUDA_CHECK(cudaEventRecord(e->ev_join2, e->side2));
+            }
+            if (tp_fused && l > 0) {
+                const void* bias = e->layers[l - 1].ffn2_b;   // (b_o + b_ffn2) / t, huggingface_convert.py:35-41,192-206
+                FTCF_TRY(ftcf_tp_gather_residual(&e->tpx, l - 1, xb[(l - 1) & 1], bias, xb[l & 1], B, st));
+                FTCF_TRY(ftcf_tp_gather_residual(&e->tpx, l - 1, l == 1 ? xb[0] : xs[(l - 1) & 1], bias, xs[l & 1], B, sb));
             }
             const ftcf_ln_prologue p2 = prologue(l, lw.ln2_g, lw.ln2_b, false);
             const ftcf_ln_prologue p1 = prologue(l, lw.ln1_g, lw.ln1_b, true);

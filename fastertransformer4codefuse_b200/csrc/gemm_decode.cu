@@ -324,11 +324,6 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             const SkPro& pro = args.pro;
             const int k = args.k, pitch = k + 8, nvec = k >> 3;
             const bool writer = pro.x_out != nullptr && blockIdx.x == 0 && blockIdx.z == 0;
-            const bool gather = pro.tpx.tp > 1;
-            // tensor-parallel gather: the previous layer's O / FFN2 tiles of every rank arrive in this rank's exchange area as
-            // flagged words; tp_gather_vec polls exactly the words it needs
-            TpIndex tpix{0, 0};
-            if (gather) tpix = tp_index(pro.tpx, pro.tp_layer);
             for (int b = 0; b < args.m; ++b) {
                 float sum = 0.f, sq = 0.f;
                 for (int base = ct; base < nvec; base += 256 * PU) {
@@ -339,7 +334,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                         v[u] = fv[u] = av[u] = bv[u] = make_uint4(0, 0, 0, 0);
                         if (vi < nvec) {
                             v[u] = *reinterpret_cast<const uint4*>(pro.x + (size_t)b * k + vi * 8);
-                            if (!gather && pro.add_ffn != nullptr) {
+                            if (pro.add_ffn != nullptr) {
                                 fv[u] = *reinterpret_cast<const uint4*>(pro.add_ffn + (size_t)b * k + vi * 8);
                                 av[u] = *reinterpret_cast<const uint4*>(pro.add_attn + (size_t)b * k + vi * 8);
                                 if (pro.add_bias != nullptr) bv[u] = ld_ro_16(pro.add_bias + vi * 8);
@@ -350,10 +345,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
                     for (int u = 0; u < PU; ++u) {
                         const int vi = base + u * 256;
                         if (vi >= nvec) continue;
-                        if (gather) {
-                            v[u] = tp_gather_vec(pro.tpx, tpix, b, vi, v[u], pro.add_bias);
-                            if (writer) *reinterpret_cast<uint4*>(pro.x_out + (size_t)b * k + vi * 8) = v[u];
-                        } else if (pro.add_ffn != nullptr) {
+                        if (pro.add_ffn != nullptr) {
                             __half2* xh = reinterpret_cast<__half2*>(&v[u]);
                             const __half2* fh = reinterpret_cast<const __half2*>(&fv[u]);
                             const __half2* ah = reinterpret_cast<const __half2*>(&av[u]);

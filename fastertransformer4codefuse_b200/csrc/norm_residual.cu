@@ -156,7 +156,7 @@ tp_gather_residual_kernel(const ftcf_tp_exchange ex, int layer, const __half* __
     const int vi = blockIdx.x * blockDim.x + threadIdx.x;
     if (vi < nvec) {
         const uint4 xv = *reinterpret_cast<const uint4*>(x + (size_t)b * ex.h + vi * 8);
-        *reinterpret_cast<uint4*>(x_out + (size_t)b * ex.h + vi * 8) = tp_gather_vec(ex, ix, b, vi, xv, bias);
+        *reinterpret_cast<uint4*>(x_out + (size_t)b * ex.h + vi * 8) = tp_gather_vec<4>(ex, ix, b, vi, xv, bias);
     }
     if (threadIdx.x == 0) trc_emit(TRC_RESIDUAL, trc_t0, trc_t1, trc_t1, ex.h, 9);
 }

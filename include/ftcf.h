@@ -124,8 +124,8 @@ int ftcf_gemm_f16_ex(const void* x, const void* w_nk, const void* bias, void* y,
  * Push side (O / FFN2 GEMM of rank r): the epilogue stores each output tile into (slot, kind, source r) of EVERY rank's area --
  * remote 8-byte stores from the kernel that computed the tile.  Data and flag travel in ONE store, so there is no fence and no
  * separate flag write on the critical path (a system-scope release after remote stores costs 6-9 us beside a streaming GEMM).
- * Gather side (fused prologue of the next QKV / FFN1 GEMM, or ftcf_tp_gather_residual): polls the words it needs until their
- * epoch is the expected one, rebuilds every rank's partial  o_r = ((ffn_r + attn_r) + bias) + half(x / tp)  with the reference's
+ * Gather side (ftcf_tp_gather_residual, one small kernel heading each branch of the next layer): polls the words it needs until
+ * their epoch is the expected one, rebuilds every rank's partial  o_r = ((ffn_r + attn_r) + bias) + half(x / tp)  with the reference's
  * fp16 adds (kernels/add_residual_kernels.cu:116-176), sums the tp partials in rank order in fp32 and rounds once: the all-reduce.
  * The exchange index g = (*step - step_base) * layer_num + layer is evaluated on the device (one captured graph serves every
  * token): slot = g & 1, epoch = g / 2 + 1.  The area is zeroed at the start of a request (epoch 0 never matches). */
@@ -142,9 +142,6 @@ typedef struct {
     float eps;
     int32_t cta_hint;   /* 0: automatic; > 0: CTAs this launch should aim for (the engine gives the two GEMMs that start a layer
                            together half of the SM slots each, so that neither queues behind the other) */
-    /* tensor-parallel gather (NULL / 0 when unused): the partials of exchange `tp_layer` replace add_ffn / add_attn */
-    const ftcf_tp_exchange* tp_exchange;
-    int32_t tp_layer;
 } ftcf_ln_prologue;
 int ftcf_gemm_w8a16_ln(const ftcf_ln_prologue* pro, const uint8_t* w_nk, const void* scale, const void* bias, void* y, int m,
                        int n, int k, int act, void* stream);

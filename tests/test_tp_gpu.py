@@ -29,4 +29,8 @@ def test_tensor_parallel_parity(cuda, world):
            "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "tp_parity.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     tail = (r.stdout + "\n" + r.stderr)[-6000:]
+    log_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(log_dir):
+        with open(os.path.join(log_dir, f"tp_parity_{world}.log"), "w") as f:
+            f.write(r.stdout + "\n---- stderr ----\n" + r.stderr[-20000:])
     assert r.returncode == 0 and "TP PARITY PASS" in r.stdout, tail

@@ -55,10 +55,12 @@ def run(op, ids, lens, out_len):
     return res[0].cpu().numpy(), res[1].cpu().numpy()
 
 
-heads = 8 if world <= 8 else world
+# every rank's slice must keep k a multiple of 128 for the int8 GEMMs: hidden / world and inter_size / world >= 128
+heads = max(8, 2 * world)
+inter = max(512, 128 * world)
 for int8_mode in (1, 0):
     for gptj in (True, False):
-        cfg = tiny_cfg(head_num=heads, use_gptj_residual=gptj)
+        cfg = tiny_cfg(head_num=heads, inter_size=inter, use_gptj_residual=gptj)
         shards = [W.make_synthetic(cfg, world, r, int8_mode, "cpu", seed=4, keep_plain=True) for r in range(world)]
         op = make_op(cfg, shards, int8_mode, gptj)
         ref = oracle_from_rank_weights(cfg, shards, int8_mode) if rank == 0 else None
@@ -82,7 +84,7 @@ for int8_mode in (1, 0):
         del op
 
 # ---- every row finishes early: end_id := the third token the oracle generates for a single-row request
-cfg = tiny_cfg(head_num=heads)
+cfg = tiny_cfg(head_num=heads, inter_size=inter)
 shards = [W.make_synthetic(cfg, world, r, 1, "cpu", seed=9, keep_plain=True) for r in range(world)]
 lens, out_len = [7], 40
 ids = prompts(cfg, lens, 7, 3)
@@ -96,7 +98,7 @@ dist.broadcast_object_list(box, src=0)
 if box[0] is None:
     report("early end_id: no usable token in the free-running continuation (test not exercised)", False)
 else:
-    cfg = tiny_cfg(head_num=heads, end_id=box[0])
+    cfg = tiny_cfg(head_num=heads, inter_size=inter, end_id=box[0])
     op = make_op(cfg, shards, 1, True)
     for graph in (1, 0):
         op.set_option("cuda_graph", graph)
