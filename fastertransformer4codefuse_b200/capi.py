@@ -26,6 +26,20 @@ class MmhaParams(C.Structure):
         ("finished", C.c_void_p), ("step", C.c_void_p), ("partial", C.c_void_p), ("counters", C.c_void_p),
         ("batch", C.c_int32), ("heads", C.c_int32), ("dh", C.c_int32), ("rotary_dim", C.c_int32),
         ("max_len", C.c_int32), ("max_input_len", C.c_int32), ("splits", C.c_int32), ("inv_sqrt_dh", C.c_float),
+        ("cache_indir", C.c_void_p), ("beam_width", C.c_int32),
+    ]
+
+
+class BeamParams(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("output_ids", C.c_void_p), ("parent_ids", C.c_void_p), ("seq_len", C.c_void_p),
+        ("finished", C.c_void_p), ("cum_log_probs", C.c_void_p), ("input_len", C.c_void_p), ("cache_indir", C.c_void_p),
+        ("stop_words", C.c_void_p), ("step", C.c_void_p), ("finished_count_host_mapped", C.c_void_p),
+        ("finished_hist_host_mapped", C.c_void_p), ("workspace", C.c_void_p),
+        ("batch", C.c_int32), ("beam_width", C.c_int32), ("vocab", C.c_int32), ("vocab_padded", C.c_int32), ("n_stop", C.c_int32),
+        ("max_input_len", C.c_int32), ("max_len", C.c_int32), ("end_id", C.c_int32),
+        ("temperature", C.c_float), ("repetition_penalty", C.c_float), ("diversity_rate", C.c_float), ("length_penalty", C.c_float),
+        ("args_differ", C.c_int32),
     ]
 
 
@@ -78,6 +92,8 @@ class GptNeoXRequest(C.Structure):
         ("temperature_host", C.c_void_p), ("n_temperature", C.c_int32),
         ("repetition_penalty_host", C.c_void_p), ("n_repetition_penalty", C.c_int32),
         ("random_seed_host", C.c_void_p), ("n_random_seed", C.c_int32),
+        ("beam_search_diversity_rate_host", C.c_void_p), ("n_beam_search_diversity_rate", C.c_int32),
+        ("len_penalty_host", C.c_void_p), ("n_len_penalty", C.c_int32),
         ("stop_words", C.c_void_p), ("n_stop", C.c_int32),
         ("optional_last_tokens", C.c_void_p), ("n_last", C.c_int32),
         ("return_cum_log_probs", C.c_int32),
@@ -136,6 +152,9 @@ SIGNATURES = {
     "ftcf_curand_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ftcf_sampling_step": (C.c_int, [C.POINTER(SamplingParams), C.c_void_p]),
     "ftcf_gather_output": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]),
+    "ftcf_beam_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "ftcf_beam_search_step": (C.c_int, [C.POINTER(BeamParams), C.c_void_p]),
+    "ftcf_gather_output_beams": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p]),
     "ftcf_gptneox_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(GptNeoXConfig), C.POINTER(C.c_void_p), C.c_size_t,
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p, C.c_void_p]),
     "ftcf_gptneox_destroy": (None, [C.c_void_p]),

@@ -31,21 +31,24 @@ const void* data_or_null(const at::Tensor& t) { return t.defined() && t.numel() 
 struct CallbackCtx {
     py::object fn;
     int end_id;
+    int beam;
     std::string error;
     bool failed = false;
 };
 
-// {"last_tokens": [[id]] * B, "idxs": [[n]] * B}, th_op/gptneox/utils/pybind_callback_utils.cc:59-103
-void token_callback(void* user, int32_t /*step*/, const int32_t* toks, const int32_t* idxs, int32_t batch)
+// {"last_tokens": [[id] * beam] * B, "idxs": [[n] * beam] * B}, th_op/gptneox/utils/pybind_callback_utils.cc:59-103
+void token_callback(void* user, int32_t /*step*/, const int32_t* toks, const int32_t* idxs, int32_t rows)
 {
     auto* ctx = static_cast<CallbackCtx*>(user);
     if (ctx->failed) return;
     try {
         py::list last_tokens, last_idxs;
-        for (int b = 0; b < batch; ++b) {
+        for (int b = 0; b < rows / ctx->beam; ++b) {
             py::list t, i;
-            t.append(py::int_(toks[b]));
-            i.append(py::int_(idxs[b]));
+            for (int j = 0; j < ctx->beam; ++j) {
+                t.append(py::int_(toks[b * ctx->beam + j]));
+                i.append(py::int_(idxs[b * ctx->beam + j]));
+            }
             last_tokens.append(t);
             last_idxs.append(i);
         }
@@ -151,8 +154,8 @@ public:
 
     std::vector<at::Tensor> forward(at::Tensor input_ids, at::Tensor input_lengths, int64_t output_len, c10::optional<int64_t> beam_width_opt,
                                     c10::optional<at::Tensor> top_k_opt, c10::optional<at::Tensor> top_p_opt,
-                                    c10::optional<at::Tensor> /*beam_search_diversity_rate_opt*/, c10::optional<at::Tensor> temperature_opt,
-                                    c10::optional<at::Tensor> /*len_penalty_opt*/, c10::optional<at::Tensor> repetition_penalty_opt,
+                                    c10::optional<at::Tensor> beam_search_diversity_rate_opt, c10::optional<at::Tensor> temperature_opt,
+                                    c10::optional<at::Tensor> len_penalty_opt, c10::optional<at::Tensor> repetition_penalty_opt,
                                     c10::optional<at::Tensor> random_seed_opt, c10::optional<at::Tensor> stop_words_list_opt,
                                     c10::optional<at::Tensor> optional_last_tokens_opt, c10::optional<int64_t> return_cum_log_probs_opt,
                                     py::object callback_opt)
@@ -167,7 +170,7 @@ public:
         TORCH_CHECK(input_ids.dim() == 2, "input_ids must be [batch, max_input_length]");
         const int64_t rcl = return_cum_log_probs_opt.has_value() ? *return_cum_log_probs_opt : 0;
         TORCH_CHECK(rcl == 0 || rcl == 1, "return_cum_log_probs should be 0 (no return cum_log_probs),  1 (the cumulative log probs of generated sequences)");
-        const int beam = beam_width_opt.has_value() ? (int)*beam_width_opt : 1;
+        const int beam = beam_width_opt.has_value() && *beam_width_opt > 1 ? (int)*beam_width_opt : 1;
         const int64_t B = input_ids.size(0), S = input_ids.size(1);
         auto opt_i32 = at::TensorOptions().dtype(at::kInt).device(input_ids.device());
         at::Tensor output_ids = at::empty({B, beam, S + output_len}, opt_i32);
@@ -195,6 +198,9 @@ public:
         host(temperature_opt, at::kFloat, p, rq.n_temperature); rq.temperature_host = static_cast<const float*>(p);
         host(repetition_penalty_opt, at::kFloat, p, rq.n_repetition_penalty); rq.repetition_penalty_host = static_cast<const float*>(p);
         host(random_seed_opt, at::kLong, p, rq.n_random_seed); rq.random_seed_host = static_cast<const int64_t*>(p);
+        host(beam_search_diversity_rate_opt, at::kFloat, p, rq.n_beam_search_diversity_rate);
+        rq.beam_search_diversity_rate_host = static_cast<const float*>(p);
+        host(len_penalty_opt, at::kFloat, p, rq.n_len_penalty); rq.len_penalty_host = static_cast<const float*>(p);
         if (stop_words_list_opt.has_value() && stop_words_list_opt->defined()) {
             at::Tensor sw = stop_words_list_opt->contiguous();
             TORCH_CHECK(sw.is_cuda() && sw.scalar_type() == at::kInt && sw.dim() == 3, "stop_words_list must be a CUDA int32 tensor [batch, 2, n]");
@@ -210,7 +216,7 @@ public:
             rq.n_last = (int32_t)ol.size(1);
         }
         rq.return_cum_log_probs = (int32_t)rcl;
-        CallbackCtx cb{callback_opt, end_id_, {}, false};
+        CallbackCtx cb{callback_opt, end_id_, beam, {}, false};
         if (!callback_opt.is_none()) {
             rq.callback = token_callback;
             rq.callback_user = &cb;

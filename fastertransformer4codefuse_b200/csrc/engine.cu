@@ -77,17 +77,19 @@ static int nccl_load()
 constexpr int NCCL_FLOAT16 = 6, NCCL_FLOAT32 = 7, NCCL_SUM = 0;
 
 // ------------------------------------------------------------------------------------------------ small kernels
-__global__ void gather_prompt_ids_kernel(int32_t* out, const int32_t* ids, const int32_t* tok_b, const int32_t* tok_p, int T, int S)
+// tok_b names the ROW (request row x beam + beam 0) a prompt token belongs to; the ids come from the request's [batch, S] tensor
+__global__ void gather_prompt_ids_kernel(int32_t* out, const int32_t* ids, const int32_t* tok_b, const int32_t* tok_p, int T, int S, int beam)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < T) out[i] = ids[(size_t)tok_b[i] * S + tok_p[i]];
+    if (i < T) out[i] = ids[(size_t)(tok_b[i] / beam) * S + tok_p[i]];
 }
-__global__ void ids_to_time_major_kernel(int32_t* out, const int32_t* ids, int B, int S)
+// rows = request batch x beam: every beam of a request starts from the same prompt (invokeTileGptInputs, kernels/gpt_kernels.cu)
+__global__ void ids_to_time_major_kernel(int32_t* out, const int32_t* ids, int rows, int S, int beam)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B * S) {
-        const int b = i / S, t = i % S;
-        out[(size_t)t * B + b] = ids[i];
+    if (i < rows * S) {
+        const int r = i / S, t = i % S;
+        out[(size_t)t * rows + r] = ids[(size_t)(r / beam) * S + t];
     }
 }
 // x[b] = table[output_ids[*step - 1][b]]  (invokeEmbeddingLookupPosEncodingPadCount, kernels/decoding_kernels.cu:260)
@@ -220,7 +222,8 @@ namespace {
 
 struct Small {   // carved out of one small device slab; all int32 / float / u8 arrays of size B (or max_len * B)
     int32_t *out_ids, *seq_len, *input_len, *pad_count, *top_k, *step, *counters, *tok_b, *tok_p, *seq_off, *last_idx, *prompt_ids,
-        *gathered, *gathered_len;
+        *gathered, *gathered_len, *parent_ids, *cache_indir;
+    int beam;                   // 1: sampling; > 1: beam search (rows = request batch x beam)
     float *top_p, *temperature, *rep_pen, *cum_log;
     uint8_t* finished;
     uint64_t* seeds;
@@ -675,6 +678,7 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
             mp.batch = B; mp.heads = e->Hl; mp.dh = dh; mp.rotary_dim = c.rotary_embedding_dim;
             mp.max_len = max_len; mp.max_input_len = S; mp.splits = splits;
             mp.inv_sqrt_dh = 1.f / std::sqrt((float)dh);
+            if (s.beam > 1) { mp.cache_indir = s.cache_indir; mp.beam_width = s.beam; }
             const bool kvpf = e->opt_two_branch && e->opt_kv_prefetch;
             if (kvpf) {   // this layer's cache rows start travelling to L2 now, while the GEMMs stream their weights
                 FTCF_CUDA_CHECK(cudaStreamWaitEvent(e->side2, e->ev_fork, 0));
@@ -772,6 +776,7 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
                 mp.batch = B; mp.heads = e->Hl; mp.dh = dh; mp.rotary_dim = c.rotary_embedding_dim;
                 mp.max_len = max_len; mp.max_input_len = S; mp.splits = splits;
                 mp.inv_sqrt_dh = 1.f / std::sqrt((float)dh);
+                if (s.beam > 1) { mp.cache_indir = s.cache_indir; mp.beam_width = s.beam; }
                 return ftcf_mmha_decode(&mp, st);
             };
             FTCF_TRY(run_layer(e, l, B, attn, e->t > 1));
@@ -802,10 +807,17 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     FTCF_REQUIRE(e && rq, FTCF_ERR_INVALID, "forward: null argument");
     const ftcf_gptneox_request& r = *rq;
     const ftcf_gptneox_config& c = e->cfg;
-    const int B = r.batch, S = r.max_input_len, out_len = r.output_len;
-    FTCF_REQUIRE(B > 0 && S >= 1 && out_len >= 1, FTCF_ERR_INVALID, "forward: batch %d, input length %d, output_len %d", B, S, out_len);
+    // Beam search (beam_width K > 1) runs the decode loop on B = batch x K rows, like the reference (GptNeoX.cc:88-156); the prompt
+    // is prefilled ONCE per request row into the cache row of beam 0 -- the cache indirection starts at 0 and only ever names
+    // other beams for generated positions (BaseBeamSearchLayer.cu:24-52), so the K - 1 redundant prefills of GptNeoX.cc:589-682
+    // are never read.
+    const int K = r.beam_width > 1 ? r.beam_width : 1;
+    const int Bq = r.batch, B = Bq * K, S = r.max_input_len, out_len = r.output_len;
+    FTCF_REQUIRE(Bq > 0 && S >= 1 && out_len >= 1, FTCF_ERR_INVALID, "forward: batch %d, input length %d, output_len %d", Bq, S, out_len);
     FTCF_REQUIRE(r.input_ids && r.input_lengths && r.output_ids && r.sequence_lengths, FTCF_ERR_INVALID, "forward: null tensor");
-    FTCF_REQUIRE(r.beam_width <= 1, FTCF_ERR_UNSUPPORTED, "forward: beam_width %d (beam search) is not implemented yet", r.beam_width);
+    FTCF_REQUIRE(K <= 32, FTCF_ERR_UNSUPPORTED, "forward: beam_width %d (supported: 1..32)", K);
+    FTCF_REQUIRE(K == 1 || S > 1, FTCF_ERR_UNSUPPORTED, "forward: beam search needs a prompt (max_input_len > 1)");
+    FTCF_REQUIRE(K == 1 || r.optional_last_tokens == nullptr, FTCF_ERR_UNSUPPORTED, "forward: optional_last_tokens with beam search");
     const int max_len = S + out_len;
     cudaStream_t st = e->stream;
     FTCF_CUDA_CHECK(cudaEventRecord(e->caller_ev, e->caller_stream));   // inputs were produced on the caller's stream
@@ -814,14 +826,15 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     const int dh = c.size_per_head, L = c.layer_num;
 
     // ---- host copies of the lengths, token bookkeeping for the padding-removed prefill (GptNeoXContextDecoder.cc:285-308)
-    std::vector<int32_t> lens(B);
-    FTCF_CUDA_CHECK(cudaMemcpyAsync(lens.data(), r.input_lengths, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> lens_q(Bq), lens(B);
+    FTCF_CUDA_CHECK(cudaMemcpyAsync(lens_q.data(), r.input_lengths, Bq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     FTCF_CUDA_CHECK(cudaStreamSynchronize(st));
     int T = 0;
-    for (int b = 0; b < B; ++b) {
-        FTCF_REQUIRE(lens[b] >= 1 && lens[b] <= S, FTCF_ERR_INVALID, "forward: input_lengths[%d] = %d outside [1, %d]", b, lens[b], S);
-        T += lens[b];
+    for (int b = 0; b < Bq; ++b) {
+        FTCF_REQUIRE(lens_q[b] >= 1 && lens_q[b] <= S, FTCF_ERR_INVALID, "forward: input_lengths[%d] = %d outside [1, %d]", b, lens_q[b], S);
+        T += lens_q[b];
     }
+    for (int b = 0; b < B; ++b) lens[b] = lens_q[b / K];
     const bool has_prefill = S > 1;
     const int m_max = has_prefill ? std::max(T, B) : B;
 
@@ -832,8 +845,9 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     int max_top_k = 1;
     bool any_temp = false, any_rep = false, any_topp = false;
     for (int b = 0; b < B; ++b) {
-        int k = r.top_k_host ? *pick(r.top_k_host, r.n_top_k, b) : 0;
-        float p = r.top_p_host ? *pick(r.top_p_host, r.n_top_p, b) : 0.f;
+        const int bq = b / K;
+        int k = r.top_k_host ? *pick(r.top_k_host, r.n_top_k, bq) : 0;
+        float p = r.top_p_host ? *pick(r.top_p_host, r.n_top_p, bq) : 0.f;
         if (k < 0) k = 0;
         if (k == 0 && p == 0.f) k = 1;
         if (k > 0 && p == 0.f) p = 1.f;
@@ -843,9 +857,9 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
         ks[b] = k;
         ps[b] = p;
         max_top_k = std::max(max_top_k, k);
-        if (r.temperature_host) temps[b] = *pick(r.temperature_host, r.n_temperature, b);
-        if (r.repetition_penalty_host) reps[b] = *pick(r.repetition_penalty_host, r.n_repetition_penalty, b);
-        if (r.random_seed_host) seeds[b] = (uint64_t)*pick(r.random_seed_host, r.n_random_seed, b);
+        if (r.temperature_host) temps[b] = *pick(r.temperature_host, r.n_temperature, bq);
+        if (r.repetition_penalty_host) reps[b] = *pick(r.repetition_penalty_host, r.n_repetition_penalty, bq);
+        if (r.random_seed_host) seeds[b] = (uint64_t)*pick(r.random_seed_host, r.n_random_seed, bq);
         any_temp |= temps[b] != 1.f;
         any_rep |= reps[b] != 1.f;
     }
@@ -868,7 +882,8 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
         FTCF_TRY(e->logits_local.ensure((size_t)B * e->Vl * 4));
         FTCF_TRY(e->logits_gather.ensure((size_t)B * e->Vp * 4));
     }
-    const size_t ws_bytes = ftcf_sampling_workspace_bytes(B, e->Vp, max_top_k) + (size_t)B * max_len * 4 + 256;
+    const size_t ws_bytes = K > 1 ? ftcf_beam_workspace_bytes(Bq, K, e->Vp, max_len)
+                                  : ftcf_sampling_workspace_bytes(B, e->Vp, max_top_k) + (size_t)B * max_len * 4 + 256;
     FTCF_TRY(e->samp_ws.ensure(ws_bytes));
     const int splits = ftcf_mmha_choose_splits(B, e->Hl, max_len);
     FTCF_TRY(e->mmha_part.ensure((size_t)B * e->Hl * splits * (dh + 2) * 4 + 256));
@@ -889,7 +904,9 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
                  o_topk = carve(B * 4), o_step = carve(4), o_cnt = carve((size_t)B * e->Hl * 4), o_seqoff = carve((B + 1) * 4),
                  o_last = carve(B * 4), o_gath = carve((size_t)B * max_len * 4), o_glen = carve(B * 4), o_topp = carve(B * 4),
                  o_temp = carve(B * 4), o_rep = carve(B * 4), o_cum = carve(B * 4), o_fin = carve(B), o_seeds = carve(B * 8),
-                 o_curand = carve((size_t)B * ftcf_curand_state_bytes()), o_tokb = carve((size_t)std::max(T, 1) * 4),
+                 o_curand = carve((size_t)B * ftcf_curand_state_bytes()),
+                 o_parent = carve(K > 1 ? (size_t)max_len * B * 4 : 0), o_indir = carve(K > 1 ? (size_t)2 * B * max_len * 4 : 0),
+                 o_tokb = carve((size_t)std::max(T, 1) * 4),
                  o_tokp = carve((size_t)std::max(T, 1) * 4), o_pids = carve((size_t)std::max(T, 1) * 4);
     FTCF_TRY(e->small.ensure(off));
     char* sb = e->small.as<char>();
@@ -900,9 +917,10 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     s.gathered = (int32_t*)(sb + o_gath); s.gathered_len = (int32_t*)(sb + o_glen); s.top_p = (float*)(sb + o_topp);
     s.temperature = (float*)(sb + o_temp); s.rep_pen = (float*)(sb + o_rep); s.cum_log = (float*)(sb + o_cum);
     s.finished = (uint8_t*)(sb + o_fin); s.seeds = (uint64_t*)(sb + o_seeds); s.curand = sb + o_curand;
+    s.parent_ids = (int32_t*)(sb + o_parent); s.cache_indir = (int32_t*)(sb + o_indir); s.beam = K;
 
     // ---- pinned staging: [lens B][pad B][seq_len B][ks B][ps B][temps B][reps B][seeds 2B][tok_b T][tok_p T][seq_off B+1][last B][step 1]
-    const size_t stage_ints = (size_t)9 * B + 2 * (size_t)std::max(T, 1) + (B + 1) + B + 1 + 2 * (size_t)B + 16;
+    const size_t stage_ints = (size_t)10 * B + 2 * (size_t)std::max(T, 1) + (B + 1) + B + 1 + 2 * (size_t)B + 16;
     if (stage_ints * 4 > e->host_stage_cap) {
         if (e->host_stage) cudaFreeHost(e->host_stage);
         e->host_stage = nullptr;
@@ -924,9 +942,10 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
         for (int b = 0; b < B; ++b) {
             pad[b] = S - lens[b];
             seq0[b] = has_prefill ? S - 1 : 0;   // invokeDecodingInitialize(max_input_length - 1), GptNeoX.cc:687-695
-            for (int p = 0; p < lens[b]; ++p) { tok_b[tix] = b; tok_p[tix] = p; ++tix; }
+            if (b % K == 0)                      // rows of beams > 0 hold no prompt tokens (empty sequences for the prefill kernels)
+                for (int p = 0; p < lens[b]; ++p) { tok_b[tix] = b; tok_p[tix] = p; ++tix; }
             seq_off[b + 1] = tix;
-            last[b] = tix - 1;
+            last[b] = tix - 1;                   // every beam starts from the last prompt token of its request row
         }
     }
     const int32_t step0 = S;
@@ -945,9 +964,17 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     FTCF_TRY(up(s.step, &step0, 4));
     FTCF_CUDA_CHECK(cudaMemsetAsync(s.finished, 0, B, st));
     FTCF_CUDA_CHECK(cudaMemsetAsync(s.cum_log, 0, B * 4, st));
+    if (K > 1) {
+        // cum_log_probs 0 for beam 0 and -1e20 for the others: the first step only expands beam 0 (decoding_kernels.cu:24-60)
+        std::vector<float> cum0(B, -1e20f);
+        for (int b = 0; b < B; b += K) cum0[b] = 0.f;
+        FTCF_TRY(up(s.cum_log, cum0.data(), (size_t)B * 4));
+        FTCF_CUDA_CHECK(cudaMemsetAsync(s.parent_ids, 0, (size_t)max_len * B * 4, st));
+        FTCF_CUDA_CHECK(cudaMemsetAsync(s.cache_indir, 0, (size_t)2 * B * max_len * 4, st));      // GptNeoX.cc:568-570
+    }
     FTCF_CUDA_CHECK(cudaMemsetAsync(s.counters, 0, (size_t)B * e->Hl * 4, st));
     FTCF_CUDA_CHECK(cudaMemsetAsync(s.out_ids, 0, (size_t)max_len * B * 4, st));
-    ids_to_time_major_kernel<<<ceil_div(B * S, 256), 256, 0, st>>>(s.out_ids, r.input_ids, B, S);
+    ids_to_time_major_kernel<<<ceil_div(B * S, 256), 256, 0, st>>>(s.out_ids, r.input_ids, B, S, K);
     FTCF_LAUNCH_CHECK();
     FTCF_TRY(ftcf_curand_init(s.curand, s.seeds, B, st));
     e->host_flag[0] = 0;
@@ -989,6 +1016,31 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     sp.has_top_p_rows = any_topp ? 1 : 0;
     sp.finished_hist_host_mapped = e->host_hist_dev;
 
+    ftcf_beam_params bp{};
+    if (K > 1) {
+        auto first = [](const float* a, int n, float dflt) { return a != nullptr && n > 0 ? a[0] : dflt; };
+        auto differ = [](const float* a, int n) {
+            for (int i = 1; a != nullptr && i < n; ++i)
+                if (a[i] != a[0]) return true;
+            return false;
+        };
+        bp.logits = e->logits.as<float>(); bp.output_ids = s.out_ids; bp.parent_ids = s.parent_ids; bp.seq_len = s.seq_len;
+        bp.finished = s.finished; bp.cum_log_probs = s.cum_log; bp.input_len = s.input_len; bp.cache_indir = s.cache_indir;
+        bp.stop_words = r.stop_words; bp.n_stop = r.stop_words ? r.n_stop : 0; bp.step = s.step;
+        bp.finished_count_host_mapped = e->host_flag_dev; bp.finished_hist_host_mapped = e->host_hist_dev; bp.workspace = e->samp_ws.p;
+        bp.batch = Bq; bp.beam_width = K; bp.vocab = c.vocab_size; bp.vocab_padded = e->Vp; bp.max_input_len = S; bp.max_len = max_len;
+        bp.end_id = c.end_id;
+        // element 0 of every runtime argument serves the whole batch (DynamicDecodeLayer.cc:308-408 hands the tensors down unsliced)
+        bp.temperature = first(r.temperature_host, r.n_temperature, 1.f);
+        bp.repetition_penalty = first(r.repetition_penalty_host, r.n_repetition_penalty, 1.f);
+        bp.diversity_rate = first(r.beam_search_diversity_rate_host, r.n_beam_search_diversity_rate, 0.f);
+        bp.length_penalty = first(r.len_penalty_host, r.n_len_penalty, 0.f);
+        bp.args_differ = (differ(r.temperature_host, r.n_temperature) || differ(r.repetition_penalty_host, r.n_repetition_penalty) ||
+                          differ(r.beam_search_diversity_rate_host, r.n_beam_search_diversity_rate) || differ(r.len_penalty_host, r.n_len_penalty))
+                             ? 1 : 0;
+    }
+    auto token_step = [&]() -> int { return K > 1 ? ftcf_beam_search_step(&bp, st) : ftcf_sampling_step(&sp, st); };
+
     cudaEvent_t ev0, ev1, ev2;
     FTCF_CUDA_CHECK(cudaEventCreate(&ev0));
     FTCF_CUDA_CHECK(cudaEventCreate(&ev1));
@@ -998,7 +1050,7 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
 
     // ---- prefill
     if (has_prefill) {
-        gather_prompt_ids_kernel<<<ceil_div(T, 256), 256, 0, st>>>(s.prompt_ids, r.input_ids, s.tok_b, s.tok_p, T, S);
+        gather_prompt_ids_kernel<<<ceil_div(T, 256), 256, 0, st>>>(s.prompt_ids, r.input_ids, s.tok_b, s.tok_p, T, S, K);
         FTCF_LAUNCH_CHECK();
         FTCF_TRY(ftcf_embedding_lookup(e->x.p, e->wte, s.prompt_ids, T, e->h, c.vocab_size, st));
         int max_seq = 0;
@@ -1035,8 +1087,9 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
 
     const bool want_trace = r.logits_trace != nullptr && r.logits_trace_steps > 0;
     const bool use_graph = e->opt_cuda_graph != 0 && out_len > 2 && !want_trace;
-    char keybuf[320];
-    snprintf(keybuf, sizeof(keybuf), "B%d S%d M%d k%d t%d r%d p%d l%p s%p n%d/%d kv%p x%p sm%p lg%p f%d g%lld", B, S, max_len, max_top_k,
+    char keybuf[400];
+    snprintf(keybuf, sizeof(keybuf), "B%d K%d:%a:%a:%a:%a:%d S%d M%d k%d t%d r%d p%d l%p s%p n%d/%d kv%p x%p sm%p lg%p f%d g%lld", B, K,
+             bp.temperature, bp.repetition_penalty, bp.diversity_rate, bp.length_penalty, bp.args_differ, S, max_len, max_top_k,
              (int)any_temp, (int)any_rep + 2 * (int)any_topp, sp.want_probs, (const void*)sp.optional_last_tokens, (const void*)sp.stop_words,
              sp.n_last, sp.n_stop, e->kv.p, e->x.p, e->small.p, e->logits.p, (int)e->fused_on + 2 * (int)(e->tp_fused && e->opt_tp_fused),
              g_capture_generation.load(std::memory_order_relaxed));
@@ -1056,7 +1109,7 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
                 const long long n0 = g_launch_count.load();
                 FTCF_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
                 int rc = decode_step(e, s, sp, B, max_len, S, splits, true);
-                if (rc == FTCF_OK) rc = ftcf_sampling_step(&sp, st);
+                if (rc == FTCF_OK) rc = token_step();
                 cudaError_t ce = cudaStreamEndCapture(st, &g);
                 if (rc != FTCF_OK) { if (g) cudaGraphDestroy(g); return rc; }
                 FTCF_CUDA_CHECK(ce);
@@ -1085,7 +1138,7 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
                                                     e->logits.as<float>() + (size_t)b * e->Vp, (size_t)c.vocab_size * 4,
                                                     cudaMemcpyDeviceToDevice, st));
             }
-            FTCF_TRY(ftcf_sampling_step(&sp, st));
+            FTCF_TRY(token_step());
         }
         ++steps_done;
         rec_step();
@@ -1125,7 +1178,11 @@ extern "C" int ftcf_gptneox_forward(ftcf_gptneox* e, const ftcf_gptneox_request*
     FTCF_CUDA_CHECK(cudaEventRecord(ev2, st));
 
     // ---- outputs (setOutputTensors, GptNeoX.cc:1090-1181)
-    FTCF_TRY(ftcf_gather_output(r.output_ids, r.sequence_lengths, s.out_ids, s.seq_len, s.input_len, B, S, max_len, c.end_id, st));
+    if (K > 1)
+        FTCF_TRY(ftcf_gather_output_beams(r.output_ids, r.sequence_lengths, s.out_ids, s.parent_ids, s.seq_len, s.input_len, Bq, K, S, max_len,
+                                          c.end_id, st));
+    else
+        FTCF_TRY(ftcf_gather_output(r.output_ids, r.sequence_lengths, s.out_ids, s.seq_len, s.input_len, B, S, max_len, c.end_id, st));
     if (r.cum_log_probs) FTCF_CUDA_CHECK(cudaMemcpyAsync(r.cum_log_probs, s.cum_log, B * 4, cudaMemcpyDeviceToDevice, st));
     FTCF_CUDA_CHECK(cudaStreamSynchronize(st));
     {

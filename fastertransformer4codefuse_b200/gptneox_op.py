@@ -110,9 +110,7 @@ class GptNeoXOp:
                 raise RuntimeError(f"{name} must be a contiguous CUDA int32 tensor")
         if input_ids.dim() != 2:
             raise RuntimeError("input_ids must be [batch, max_input_length]")
-        bw = 1 if beam_width is None else int(beam_width)
-        if bw != 1:
-            raise RuntimeError("beam_width > 1 (beam search) is not implemented yet")
+        bw = 1 if beam_width is None else max(1, int(beam_width))
         rcl = 0 if return_cum_log_probs is None else int(return_cum_log_probs)
         if rcl not in (0, 1):                                        # GptNeoXOp.cc:143-145
             raise RuntimeError("return_cum_log_probs should be 0 (no return cum_log_probs), "
@@ -141,6 +139,8 @@ class GptNeoXOp:
         rq.temperature_host, rq.n_temperature = host(temperature, torch.float32)
         rq.repetition_penalty_host, rq.n_repetition_penalty = host(repetition_penalty, torch.float32)
         rq.random_seed_host, rq.n_random_seed = host(random_seed, torch.int64)
+        rq.beam_search_diversity_rate_host, rq.n_beam_search_diversity_rate = host(beam_search_diversity_rate, torch.float32)
+        rq.len_penalty_host, rq.n_len_penalty = host(len_penalty, torch.float32)
         if stop_words_list is not None:
             if not (stop_words_list.is_cuda and stop_words_list.dtype == torch.int32 and stop_words_list.dim() == 3):
                 raise RuntimeError("stop_words_list must be a CUDA int32 tensor [batch, 2, n]")
@@ -163,7 +163,8 @@ class GptNeoXOp:
         if callback is not None:
             def _cb(_user, _step, toks, idxs, n):
                 try:    # same message shape as th_op/gptneox/utils/pybind_callback_utils.cc:59-103
-                    callback({"last_tokens": [[int(toks[i])] for i in range(n)], "idxs": [[int(idxs[i])] for i in range(n)]})
+                    callback({"last_tokens": [[int(toks[b * bw + j]) for j in range(bw)] for b in range(n // bw)],
+                              "idxs": [[int(idxs[b * bw + j]) for j in range(bw)] for b in range(n // bw)]})
                 except BaseException as exc:   # noqa: BLE001 -- must not unwind through C
                     cb_err.append(exc)
             cfn = capi.TOKEN_CALLBACK(_cb)

@@ -193,6 +193,11 @@ typedef struct {
     int32_t* counters;          /* [B*heads] zero-initialised, self-resetting                                 */
     int32_t batch, heads, dh, rotary_dim, max_len, max_input_len, splits;
     float inv_sqrt_dh;
+    /* beam search (NULL / 0 otherwise): batch counts batch x beam rows; slot t < seq_len of row r is read from cache row
+     * (r / beam_width) * beam_width + cache_indir[parity][r][t], parity = (*step - max_input_len) & 1 -- the buffer the previous
+     * beam-search step wrote (template.hpp:1494-1522,1709-1761; double buffer GptNeoX.cc:118-122,777-778) */
+    const int32_t* cache_indir; /* [2, B, max_len] */
+    int32_t beam_width;
 } ftcf_mmha_params;
 int ftcf_mmha_decode(const ftcf_mmha_params* p, void* stream);
 /* Optional companion of ftcf_mmha_decode: L2 prefetch of the cache rows that launch will read (same params; only the cache
@@ -253,6 +258,39 @@ int ftcf_gather_output(int32_t* out /* [B, max_len] */, int32_t* out_len /* [B] 
                        int end_id, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Online beam search (beam_width > 1): layers/DynamicDecodeLayer.cc:308-408 -> layers/beam_search_layers/BaseBeamSearchLayer.cu:170-285
+ * -> OnlineBeamSearchLayer.cu:83-170.  Rows are batch x beam ("B*K").
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    float* logits;                 /* [B*K, vocab_padded] fp32, modified in place by the penalties                   */
+    int32_t* output_ids;           /* [max_len, B*K] time-major                                                      */
+    int32_t* parent_ids;           /* [max_len, B*K] time-major: the beam slot each token's history continues in     */
+    int32_t* seq_len;              /* [B*K]                                                                          */
+    uint8_t* finished;             /* [B*K]                                                                          */
+    float* cum_log_probs;          /* [B*K]; initial state 0 for beam 0, -1e20 for the others (decoding_kernels.cu:24-60) */
+    const int32_t* input_len;      /* [B*K] (tiled)                                                                  */
+    int32_t* cache_indir;          /* [2, B*K, max_len], zero-initialised; see ftcf_mmha_params                      */
+    const int32_t* stop_words;     /* [B, 2, n_stop] or NULL                                                         */
+    int32_t* step;                 /* device scalar, read; advanced by one at the end                                */
+    int32_t* finished_count_host_mapped;  /* as in ftcf_sampling_params (counts rows, i.e. up to B*K)                */
+    int32_t* finished_hist_host_mapped;
+    void* workspace;               /* ftcf_beam_workspace_bytes()                                                    */
+    int32_t batch, beam_width, vocab, vocab_padded, n_stop, max_input_len, max_len, end_id;
+    float temperature, repetition_penalty, diversity_rate, length_penalty;
+    int32_t args_differ;           /* 1: the runtime arguments differ between rows; the reference then runs the batches one by
+                                      one, which only changes which row's length the length penalty looks at (b * K instead of b) */
+} ftcf_beam_params;
+size_t ftcf_beam_workspace_bytes(int batch, int beam_width, int vocab_padded, int max_len);
+/* One decoding step: penalties (kernels/beam_search_penalty_kernels.cu), log-softmax + 2K candidates per row, K winners per
+ * batch (kernels/online_softmax_beamsearch_kernels.cu), update of ids / parents / lengths / finished flags, cache indirection,
+ * stop words (kernels/stop_criteria_kernels.cu:24-84), finished count; *step += 1. */
+int ftcf_beam_search_step(const ftcf_beam_params* p, void* stream);
+/* gatherTree with parents (kernels/decoding_kernels.cu:452-580): out [B, K, max_len], out_len [B, K]. */
+int ftcf_gather_output_beams(int32_t* out, int32_t* out_len, const int32_t* ids_time_major, const int32_t* parent_ids,
+                             const int32_t* seq_len, const int32_t* input_len, int batch, int beam_width, int max_input_len,
+                             int max_len, int end_id, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Model-level engine: the request loop of ft::GptNeoX<T>::forward (models/gptneox/GptNeoX.cc:385-1052) with
  * GptNeoXContextDecoder (…ContextDecoder.cc:223-512) and GptNeoXDecoder (…Decoder.cc:197-389) underneath.
  * ---------------------------------------------------------------------------------------------- */
@@ -277,8 +315,8 @@ int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config* cfg, cons
 void ftcf_gptneox_destroy(ftcf_gptneox* h);
 int ftcf_nccl_unique_id(void* out128);
 
-typedef void (*ftcf_token_callback)(void* user, int32_t step, const int32_t* last_tokens_host /* [B] */,
-                                    const int32_t* idxs_host /* [B] */, int32_t batch);
+typedef void (*ftcf_token_callback)(void* user, int32_t step, const int32_t* last_tokens_host /* [B * beam] */,
+                                    const int32_t* idxs_host /* [B * beam] */, int32_t rows /* B * beam */);
 typedef struct {
     const int32_t* input_ids;       /* device [B, S]                                                         */
     const int32_t* input_lengths;   /* device [B]                                                            */
@@ -290,14 +328,17 @@ typedef struct {
     const float* temperature_host; int32_t n_temperature;
     const float* repetition_penalty_host; int32_t n_repetition_penalty;
     const int64_t* random_seed_host; int32_t n_random_seed;
+    /* beam search only (beam_width > 1): element 0 applies to the whole batch, as in the reference (DynamicDecodeLayer.cc:308-408) */
+    const float* beam_search_diversity_rate_host; int32_t n_beam_search_diversity_rate;
+    const float* len_penalty_host; int32_t n_len_penalty;
     const int32_t* stop_words;      /* device [B, 2, n_stop] or NULL */ int32_t n_stop;
     const int32_t* optional_last_tokens; /* device [B, n_last] or NULL */ int32_t n_last;
     int32_t return_cum_log_probs;
     ftcf_token_callback callback;   /* may be NULL */ void* callback_user;
     /* outputs (device) */
-    int32_t* output_ids;            /* [B, 1, S + output_len]                                                */
-    int32_t* sequence_lengths;      /* [B, 1]                                                                */
-    float* cum_log_probs;           /* [B, 1] or NULL                                                        */
+    int32_t* output_ids;            /* [B, beam, S + output_len]                                             */
+    int32_t* sequence_lengths;      /* [B, beam]                                                             */
+    float* cum_log_probs;           /* [B, beam] or NULL                                                     */
     /* optional debug taps (device, may be NULL): fp32 logits of every step [steps, B, vocab]                */
     float* logits_trace;  int32_t logits_trace_steps;
 } ftcf_gptneox_request;

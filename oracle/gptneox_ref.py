@@ -399,3 +399,143 @@ class GptNeoXRef:
         if keep_logits:
             res["logits"] = logits_trace
         return res
+
+    # ------------------------------------------------------------------------------------------- beam search (beam_width > 1)
+    def forward_beam(self, input_ids, input_lengths, output_len, beam_width, temperature=None, repetition_penalty=None,
+                     beam_search_diversity_rate=None, len_penalty=None, stop_words_list=None, decide_on_logits=None):
+        """GptNeoX.cc:385-1052 with beam_width > 1: inputs tiled over the beams (invokeTileGptInputs), prefill and decode on
+        batch x beam rows, decode attention through the cache indirection (template.hpp:1494-1522,1709-1761), the online beam
+        search of oracle/beam_search_ref.py, gatherTree with parents.  Runtime arguments: element 0 is used for every row
+        (DynamicDecodeLayer.cc:308-408 passes the tensors down unsliced).
+        decide_on_logits [steps, B*K, vocab] (optional): the beam decisions are taken on THESE logits (e.g. the ones a device run
+        traced) while the model's own logits are still computed and returned in "logits" -- a comparison that does not hinge on
+        near-ties between candidates (random small models give score gaps of 1e-3, the size of fp16 noise)."""
+        from oracle import beam_search_ref as BS
+        cfg = self.cfg
+        t = cfg.tensor_para_size
+        L, H, Dh, rot = cfg.layer_num, cfg.head_num, cfg.size_per_head, cfg.rotary_embedding_dim
+        Hl = H // t
+        hl = Hl * Dh
+        K = int(beam_width)
+        input_ids = np.repeat(np.asarray(input_ids, dtype=np.int64), K, axis=0)      # [B*K, S]
+        lens = np.repeat(np.asarray(input_lengths, dtype=np.int64), K)
+        BB, S_in = input_ids.shape
+        B = BB // K
+        maxlen = S_in + output_len
+        wte = self.ranks[0].w[12 * L].float()
+        lnf_g, lnf_b = self.ranks[0].w[12 * L + 1], self.ranks[0].w[12 * L + 2]
+        lm_head = self.ranks[0].w[12 * L + 3].float()
+        Vp = self.vocab_padded
+        inv_sqrt_dh = 1.0 / math.sqrt(Dh)
+        first = lambda a, d: float(np.asarray(d if a is None else a, np.float32).reshape(-1)[0])
+        temp, rep = first(temperature, 1.0), first(repetition_penalty, 1.0)
+        div, lp = first(beam_search_diversity_rate, 0.0), first(len_penalty, 0.0)
+
+        kc = [[torch.zeros(BB, Hl, maxlen, Dh) for _ in range(L)] for _ in range(t)]
+        vc = [[torch.zeros(BB, Hl, maxlen, Dh) for _ in range(L)] for _ in range(t)]
+        out_ids = np.zeros((maxlen, BB), dtype=np.int64)
+        out_ids[:S_in] = input_ids.T
+        parent_ids = np.zeros((maxlen, BB), dtype=np.int64)
+        seq_len = np.full(BB, S_in - 1, dtype=np.int64)
+        finished, cum_log = BS.decoding_initialize(B, K)
+        indir = [np.zeros((BB, maxlen), dtype=np.int64), np.zeros((BB, maxlen), dtype=np.int64)]
+        masked = np.zeros((BB, maxlen), dtype=bool)
+        for b in range(BB):
+            masked[b, lens[b]:S_in] = True
+        pad_count = np.zeros(BB, dtype=np.int64)
+        margins = []                       # per step and batch: the smallest score gap among the K + 1 best candidates
+        logits_trace, finished_trace = [], []
+
+        def bias_rotary(r, l, qkv, pos):
+            qkv = h(qkv + self._W(r, 3, l).float())
+            q, k, v = [z.reshape(-1, Hl, Dh) for z in qkv.split(hl, dim=-1)]
+            cos, sin = rotary_coef(pos, rot)
+            q = apply_rotary_neox(q, cos[:, None, :], sin[:, None, :], rot)
+            k = apply_rotary_neox(k, cos[:, None, :], sin[:, None, :], rot)
+            return q, k, v
+
+        assert S_in > 1, "the beam-search restatement covers requests with a prompt (max_input_length > 1)"
+        tok_b = np.concatenate([np.full(lens[b], b) for b in range(BB)])
+        tok_p = np.concatenate([np.arange(lens[b]) for b in range(BB)])
+        x = h(wte[torch.from_numpy(input_ids[tok_b, tok_p])])
+        offs = np.concatenate([[0], np.cumsum(lens)])
+
+        def ctx_attn(r, l, qkv):
+            q, k, v = bias_rotary(r, l, qkv, torch.from_numpy(tok_p))
+            ctx = torch.zeros(q.shape[0], Hl, Dh)
+            for b in range(BB):
+                s, e = offs[b], offs[b + 1]
+                n = e - s
+                kc[r][l][b, :, :n] = k[s:e].transpose(0, 1)
+                vc[r][l][b, :, :n] = v[s:e].transpose(0, 1)
+                qb, kb, vb = q[s:e].transpose(0, 1), k[s:e].transpose(0, 1), v[s:e].transpose(0, 1)
+                sc = (qb @ kb.transpose(1, 2))
+                mask = torch.tril(torch.ones(n, n)) == 0
+                sc = sc * h(torch.tensor(inv_sqrt_dh)) + mask * (-10000.0)
+                p = h(torch.softmax(sc, dim=-1))
+                ctx[s:e] = h(p @ vb).transpose(0, 1)
+            return ctx.reshape(-1, hl)
+
+        for l in range(L):
+            x = self._layer(x, l, ctx_attn)
+        x_last = x[torch.from_numpy(offs[1:] - 1)]
+
+        steps_done = 0
+        for step in range(S_in, maxlen):
+            src, tgt = indir[(step - S_in) % 2], indir[1 - (step - S_in) % 2]
+            if step != S_in:
+                ids_prev = out_ids[step - 1]
+                x = h(wte[torch.from_numpy(ids_prev)])
+                tl = seq_len.copy()
+                pos = torch.from_numpy((step - 1) - pad_count)
+
+                def dec_attn(r, l, qkv):
+                    q, k, v = bias_rotary(r, l, qkv, pos)
+                    ctx = torch.zeros(BB, Hl, Dh)
+                    for bb in range(BB):
+                        if finished[bb]:
+                            continue
+                        tlen = int(tl[bb])
+                        kc[r][l][bb, :, tlen] = k[bb]
+                        vc[r][l][bb, :, tlen] = v[bb]
+                    for bb in range(BB):
+                        if finished[bb]:
+                            continue
+                        tlen = int(tl[bb])
+                        rows = torch.from_numpy((bb // K) * K + src[bb, :tlen + 1])
+                        rows[tlen] = bb                                              # the new token's slot is the row's own
+                        ar = torch.arange(tlen + 1)
+                        keys = kc[r][l][rows, :, ar].transpose(0, 1)                 # [Hl, tlen+1, Dh]
+                        vals = vc[r][l][rows, :, ar].transpose(0, 1)
+                        sc = (keys @ q[bb][:, :, None]).squeeze(-1) * inv_sqrt_dh
+                        mk = torch.from_numpy(masked[bb, :tlen + 1])
+                        sc_m = sc.masked_fill(mk[None, :], float("-inf"))
+                        mx = sc_m.max(dim=-1, keepdim=True).values
+                        e = torch.exp(sc - mx).masked_fill(mk[None, :], 0.0)
+                        p = h(e * (1.0 / (e.sum(-1, keepdim=True) + 1e-6)))
+                        ctx[bb] = h((p[:, None, :] @ vals).squeeze(1))
+                    return ctx.reshape(BB, hl)
+
+                for l in range(L):
+                    x = self._layer(x, l, dec_attn)
+                x_last = x
+            finished_trace.append(finished.copy())
+            n = layernorm_ref(x_last, lnf_g, lnf_b, cfg.layernorm_eps)
+            logits = torch.zeros(BB, Vp)
+            logits[:, :cfg.vocab_size] = n @ lm_head.t()
+            logits = logits.numpy().astype(np.float32)
+            logits_trace.append(logits[:, :cfg.vocab_size].copy())
+            if decide_on_logits is not None:
+                logits = np.zeros((BB, Vp), dtype=np.float32)
+                logits[:, :cfg.vocab_size] = np.asarray(decide_on_logits[steps_done], dtype=np.float32)
+            BS.beam_step(logits, step, out_ids, parent_ids, seq_len, finished, cum_log, src, tgt, lens, S_in, K, cfg.vocab_size,
+                         cfg.end_id, temp, rep, div, lp, stop_words_list, margins)
+            steps_done += 1
+            if finished.all():
+                break
+            if step == S_in:
+                pad_count = S_in - lens
+        output, out_len = BS.gather_tree(out_ids, parent_ids, seq_len, lens, S_in, maxlen, cfg.end_id, K)
+        return {"output_ids": output, "sequence_lengths": out_len, "cum_log_probs": cum_log.reshape(B, K).copy(),
+                "raw_output_ids": out_ids, "parent_ids": parent_ids, "steps": steps_done, "min_margin": min(margins),
+                "logits": logits_trace, "finished_before": finished_trace}

@@ -11,7 +11,9 @@
 //   kernels/sampling_topp_kernels.cu            invokeTopPInitialize + invokeBatchTopPSampling (pure top-p rows)
 //   kernels/stop_criteria_kernels.cu            invokeStopWordsCriterion
 //   kernels/unfused_attention_kernels.cu        invokeAddFusedQKVBiasTranspose (prefill bias + NeoX rotary + split), invokeMaskedSoftmax
-//   kernels/decoding_kernels.cu                 invokeGatherTree (output gather with the pad gap removed)
+//   kernels/decoding_kernels.cu                 invokeGatherTree (output gather with the pad gap removed; with parents for beams)
+//   kernels/beam_search_penalty_kernels.cu      invokeAddBiasApplyPenalties (temperature / repetition penalty along the beam history)
+//   kernels/online_softmax_beamsearch_kernels.cu invokeTopkSoftMax (log-softmax + 2K candidates per row + K winners per batch)
 // so that `-m gpu` tests can compare our kernels with the reference's on the same inputs on the B200 (tests/test_ref_kernels_gpu.py).
 // Nothing here is part of the product; no reference source is copied.
 #include <cuda_fp16.h>
@@ -28,6 +30,8 @@
 #include "src/fastertransformer/kernels/sampling_topp_kernels.h"
 #include "src/fastertransformer/kernels/stop_criteria_kernels.h"
 #include "src/fastertransformer/kernels/decoding_kernels.h"
+#include "src/fastertransformer/kernels/beam_search_penalty_kernels.h"
+#include "src/fastertransformer/kernels/online_softmax_beamsearch_kernels.h"
 #include "src/fastertransformer/kernels/unfused_attention_kernels.h"
 #include "src/fastertransformer/utils/Tensor.h"
 #include "src/fastertransformer/utils/logger.h"
@@ -230,6 +234,62 @@ extern "C" int ref_gather_tree_sampling(int* output_ids, int* sequence_lengths, 
     param.beam_width = 1;
     param.step_ids = step_ids;
     param.parent_ids = nullptr;
+    param.end_tokens = end_tokens;
+    param.max_input_length = max_input_length;
+    param.prefix_soft_prompt_lengths = nullptr;
+    param.input_lengths = input_lengths;
+    param.max_prefix_soft_prompt_length = 0;
+    param.max_input_without_prompt_length = max_input_length;
+    param.stream = S(stream);
+    param.output_ids = output_ids;
+    ft::invokeGatherTree(param);
+    return done();
+}
+
+// ---- beam search (beam_width > 1), as layers/beam_search_layers/BaseBeamSearchLayer.cu:228-262 and OnlineBeamSearchLayer.cu:124-142
+// call them (no BeamHypotheses: models/gptneox/GptNeoX.cc passes none).
+extern "C" int ref_beam_penalties(float* logits, int step, const int* output_ids, const int* parent_ids, const int* input_lengths,
+                                  const int* sequence_lengths, int max_input_length, int batch, int beam_width, int vocab, int vocab_padded,
+                                  const int* end_ids, float temperature, float repetition_penalty, void* stream)
+{
+    const ft::RepetitionPenaltyType type = repetition_penalty != 1.0f ? ft::RepetitionPenaltyType::Multiplicative : ft::RepetitionPenaltyType::None;
+    ft::invokeAddBiasApplyPenalties<float>(step, logits, output_ids + (size_t)(step - 1) * batch * beam_width, output_ids, parent_ids,
+                                           input_lengths, sequence_lengths, (const float*)nullptr, 0, max_input_length, batch, batch, beam_width,
+                                           vocab, vocab_padded, end_ids, temperature, repetition_penalty, type, 0, S(stream));
+    return done();
+}
+
+// ids [batch * beam_width] receives row * vocab_padded + token of the K winners per batch; cum_log_probs is updated in place.
+// workspace: floats, sized as OnlineBeamSearchLayer.cu:175-182.
+extern "C" size_t ref_beam_topk_workspace_floats(int batch)
+{
+    return (size_t)(ceil(batch * 64 * (64 * 2) / 4.) * 4 * 2 + ceil(batch * (64 * 2) * 128 * (2 * (4 * 2) + 2) / 4.) * 4);
+}
+extern "C" int ref_beam_topk_softmax(const float* logits, const void* finished, const int* sequence_lengths, float* cum_log_probs, int* ids,
+                                     void* workspace, size_t workspace_floats, int batch, int beam_width, int vocab_padded, const int* end_ids,
+                                     float diversity_rate, float length_penalty, void* stream)
+{
+    ft::BeamHypotheses hyps;
+    ft::invokeTopkSoftMax<float>(logits, (const float*)nullptr, static_cast<const bool*>(finished), sequence_lengths, cum_log_probs,
+                                 (float*)nullptr, ids, workspace, (int)workspace_floats, &hyps, batch, beam_width, vocab_padded, end_ids,
+                                 diversity_rate, length_penalty, S(stream));
+    return done();
+}
+
+// output_ids [B, beam, max_time] <- time-major step_ids / parent_ids, as GptNeoX<T>::setOutputTensors (models/gptneox/GptNeoX.cc:1141-1164)
+extern "C" int ref_gather_tree_beams(int* output_ids, int* sequence_lengths, int* scratch, int max_time, int batch, int beam_width,
+                                     const int* step_ids, const int* parent_ids, const int* end_tokens, const int* input_lengths,
+                                     int max_input_length, void* stream)
+{
+    ft::gatherTreeParam param;
+    param.beams = scratch;
+    param.max_sequence_lengths = sequence_lengths;
+    param.max_sequence_length_final_step = 1;
+    param.max_time = max_time;
+    param.batch_size = batch;
+    param.beam_width = beam_width;
+    param.step_ids = step_ids;
+    param.parent_ids = parent_ids;
     param.end_tokens = end_tokens;
     param.max_input_length = max_input_length;
     param.prefix_soft_prompt_lengths = nullptr;
