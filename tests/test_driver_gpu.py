@@ -4,7 +4,10 @@ where it lies into oracle/_ref/codefuse_example.pyc by oracle/Makefile -- the GP
 (libth_gptneox.so / libth_common.so), a two-layer checkpoint directory written by our converter (checkpoint.py ==
 huggingface_convert.py's files) and a small word-level tokenizer directory.  Its printed generations must be the oracle's tokens,
 decoded by the same tokenizer, for int8_mode 0 and 1 (the driver quantises at load through OUR libth_common) and for pre-quantised
-*.q.bin / *.s.bin files (enable_int8_weights = 1)."""
+*.q.bin / *.s.bin files (enable_int8_weights = 1).  The last request is a beam search (beam_width 3, as line 3 of the reference's
+input_demo.jsonl, streamed through the callback): its three printed beams must be what our ctypes GptNeoXOp gives in this process on
+the same checkpoint (the beam search itself is pinned against the oracle and the reference's kernels in tests/test_beam_search_gpu.py;
+a free-running oracle comparison would hinge on 1e-3 score gaps of this random model)."""
 import json
 import os
 import socket
@@ -113,6 +116,8 @@ def test_unchanged_reference_driver(cuda, tmp_path, int8_mode, enable_int8_weigh
         {"prompts": [{"prompt": text(prompts[1]), "top_k": 1}, {"prompt": text(prompts[2]), "top_k": 1}], "out_seq_length": 6},   # ragged batch
         {"prompts": [{"prompt": text(prompts[0]), "top_k": 40, "top_p": 0.9, "temperature": 0.2, "repetition_penalty": 1.1,
                       "random_seed": 7}], "out_seq_length": 8},                                                    # input_demo.jsonl-style sampling
+        {"prompts": [{"prompt": text(prompts[1])}, {"prompt": text(prompts[2])}], "out_seq_length": 6, "beam_width": 3,
+         "stream": True},                                                                                        # beam search, streamed
     ]
     got, out = _run_driver(tmp_path, ckpt, tmp_path / "tok", requests, int8_mode, enable_int8_weights)
     ref = _oracle(fp_dir, int8_mode)
@@ -129,4 +134,22 @@ def test_unchanged_reference_driver(cuda, tmp_path, int8_mode, enable_int8_weigh
     want = expect([prompts[0]], 8, top_k=[1], top_p=[0.0])
     want += expect([prompts[1], prompts[2]], 6, top_k=[1, 1], top_p=[0.0, 0.0])
     want += expect([prompts[0]], 8, top_k=[40], top_p=[0.9], temperature=[0.2], repetition_penalty=[1.1], random_seed=[7])
-    assert got == want, f"driver printed {got}\noracle gives {want}\n---- driver output ----\n{out[-3000:]}"
+    # beam request: the same engine through the ctypes mirror of the op, on the same checkpoint files
+    from fastertransformer4codefuse_b200.gptneox_op import GptNeoXOp
+    dev = cuda
+    cfg2, w2, q2, s2 = CK.load_rank(ckpt, 0, 1, int8_mode=int8_mode, enable_int8_weights=bool(enable_int8_weights))
+    op = GptNeoXOp(None, 0, cfg2.head_num, cfg2.size_per_head, cfg2.inter_size, cfg2.layer_num, cfg2.vocab_size, cfg2.rotary_embedding_dim,
+                   cfg2.start_id, cfg2.end_id, 1, 1, int8_mode, 1024, bool(cfg2.use_gptj_residual),
+                   [x.to(dev) for x in w2], [x.to(dev) for x in q2], [x.to(dev) for x in s2])
+    S = max(len(prompts[1]), len(prompts[2]))
+    bid = np.full((2, S), EOS, dtype=np.int32)
+    bid[0, :len(prompts[1])], bid[1, :len(prompts[2])] = prompts[1], prompts[2]
+    res = op.forward(torch.from_numpy(bid).to(dev), torch.tensor([len(prompts[1]), len(prompts[2])], dtype=torch.int32, device=dev), 6,
+                     beam_width=3)[0].cpu().numpy()
+    for b, n in enumerate((len(prompts[1]), len(prompts[2]))):
+        for j in range(3):
+            gen = [int(t) for t in res[b, j, n:]]
+            gen = gen[:gen.index(EOS)] if EOS in gen else gen
+            want.append(tok.decode(gen))
+    assert len(got) == len(want) == 4 + 6
+    assert got == want, f"driver printed {got}\nexpected {want}\n---- driver output ----\n{out[-3000:]}"
