@@ -56,7 +56,7 @@ struct MmhaP {
     int prefetch;
 };
 
-template <int DH>
+template <int DH, bool BEAMS = false>
 __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP params)
 {
     const ftcf_mmha_params& p = params.p;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
     // QKV GEMM that is still running, so the DRAM latency of the rows hides behind that kernel's tail and the loads after the
     // wait are L2 hits.  (Keeping the rows in registers instead was measured slower: at 128 registers x 256 threads only two
     // CTAs fit per SM next to the GEMM CTAs and the grid ran in waves.)
-    for (int pos = start + (tid >> 1); pos < end && params.prefetch && p.cache_indir == nullptr; pos += MMHA_THREADS / 2) {
+    for (int pos = start + (tid >> 1); pos < end && params.prefetch && !BEAMS; pos += MMHA_THREADS / 2) {
         if (pos == tlen || (pos >= in_len && pos < max_in)) continue;
         const __half* src = ((tid & 1) ? vc : kc) + (size_t)pos * DH;
 #pragma unroll
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
     // beam-search step wrote); the new token goes to the row's own slot (template.hpp:1494-1522,1709-1761).
     const int32_t* indir = nullptr;
     const __half *kc0 = kc, *vc0 = vc;        // cache of beam 0 of this row's batch, head h
-    if (p.cache_indir != nullptr) {
+    if constexpr (BEAMS) {
         indir = p.cache_indir + ((size_t)((*p.step - p.max_input_len) & 1) * p.batch + b) * p.max_len;
         const int beam0 = (b / p.beam_width) * p.beam_width;
         kc0 = static_cast<const __half*>(p.k_cache) + ((size_t)beam0 * H + h) * (size_t)p.max_len * DH;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
             kv[u] = make_uint4(0, 0, 0, 0);
             if (valid[u]) {
                 if (pos == tlen) kv[u] = *reinterpret_cast<const uint4*>(&s_k[li * 8]);
-                else if (indir != nullptr) kv[u] = ld_stream_16(kc0 + (size_t)indir[pos] * beam_stride + (size_t)pos * DH + li * 8);
+                else if (BEAMS) kv[u] = ld_stream_16(kc0 + (size_t)indir[pos] * beam_stride + (size_t)pos * DH + li * 8);
                 else kv[u] = ld_stream_16(kc + (size_t)pos * DH + li * 8);
             }
         }
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(MMHA_THREADS) mmha_decode_kernel(const MmhaP p
             vv[u] = make_uint4(0, 0, 0, 0);
             if (pr[u] != 0.f) {
                 if (pos == tlen) vv[u] = *reinterpret_cast<const uint4*>(&s_v[li * 8]);
-                else if (indir != nullptr) vv[u] = ld_stream_16(vc0 + (size_t)indir[pos] * beam_stride + (size_t)pos * DH + li * 8);
+                else if (BEAMS) vv[u] = ld_stream_16(vc0 + (size_t)indir[pos] * beam_stride + (size_t)pos * DH + li * 8);
                 else vv[u] = ld_stream_16(vc + (size_t)pos * DH + li * 8);
             }
         }
@@ -1163,9 +1163,9 @@ extern "C" int ftcf_mmha_decode(const ftcf_mmha_params* p, void* stream)
         FTCF_REQUIRE(p->beam_width > 1 && p->batch % p->beam_width == 0, FTCF_ERR_INVALID, "mmha: cache_indir with beam_width %d, %d rows",
                      p->beam_width, p->batch);
         switch (p->dh) {
-            case 64: lerr = launch_pdl_if(pdl, mmha_decode_kernel<64>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
-            case 128: lerr = launch_pdl_if(pdl, mmha_decode_kernel<128>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
-            case 256: lerr = launch_pdl_if(pdl, mmha_decode_kernel<256>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
+            case 64: lerr = launch_pdl_if(pdl, mmha_decode_kernel<64, true>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
+            case 128: lerr = launch_pdl_if(pdl, mmha_decode_kernel<128, true>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
+            case 256: lerr = launch_pdl_if(pdl, mmha_decode_kernel<256, true>, grid, dim3(MMHA_THREADS), 0, as_stream(stream), mp); break;
             default: FTCF_REQUIRE(false, FTCF_ERR_UNSUPPORTED, "mmha: size_per_head %d (supported: 64, 128, 256)", p->dh);
         }
         FTCF_REQUIRE(lerr == cudaSuccess, FTCF_ERR_CUDA, "mmha (beams) launch failed: %s", cudaGetErrorString(lerr));

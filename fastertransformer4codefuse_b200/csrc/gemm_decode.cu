@@ -646,6 +646,9 @@ int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, con
     // (rounded to nearest: 80 tiles against a target of 148 take two splits, not one)
     int S = std::max(1, std::min((target + tiles / 2) / tiles, kb_all / std::max(1, g_dg_min_kb.load(std::memory_order_relaxed))));
     S = std::min(S, 16);
+    // never more CTAs than co-resident slots (2 per SM): a second wave of a few CTAs doubles the launch's duration
+    // (n = 20480 at target 296: 320 CTAs ran 36.9 us under ncu, profiles/r2_gemm_decode_ncu_full.txt)
+    while (S > 1 && tiles * S > 2 * 148) --S;
     dg::Args a{};
     a.scale = static_cast<const __half*>(scale);
     a.bias = static_cast<const __half*>(bias);

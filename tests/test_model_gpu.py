@@ -179,7 +179,9 @@ def test_argument_errors_raise(cuda):
     with pytest.raises(RuntimeError):
         op.forward(ids32, torch.tensor([9], dtype=torch.int32, device=cuda), 4)      # length > max_input_length
     with pytest.raises(RuntimeError):
-        op.forward(ids32, torch.tensor([4], dtype=torch.int32, device=cuda), 4, 3)   # beam search not there yet
+        op.forward(ids32, torch.tensor([4], dtype=torch.int32, device=cuda), 4, 33)  # beam_width beyond the supported 32
+    with pytest.raises(RuntimeError):                                                 # beam search needs a prompt to tile
+        op.forward(ids32[:, :1].contiguous(), torch.tensor([1], dtype=torch.int32, device=cuda), 4, 3)
 
 
 def test_pybind_shim_runs_the_reference_call(cuda):
