@@ -145,6 +145,23 @@ def quantize_dir(in_dir: str, out_dir: str, tensor_para_size: int) -> None:
                 q, s = quant.symmetric_quantize_last_axis_of_batched_matrix_int8(w)
                 q.numpy().tofile(stem + ".q.bin")
                 s.numpy().tofile(stem + ".s.bin")
+    # the *.q.bin bytes are in the B200 layout (W^T, k contiguous, q + 128), NOT the reference's sm80 interleaved layout: say so in
+    # config.ini (an extra key the reference driver ignores), so that a loader given the wrong FTCF_INT8_LAYOUT fails loudly
+    ini = configparser.ConfigParser()
+    ini.read(os.path.join(out_dir, "config.ini"))
+    ini["gptneox"][INT8_LAYOUT_KEY] = "b200"
+    with open(os.path.join(out_dir, "config.ini"), "w") as f:
+        ini.write(f)
+
+
+INT8_LAYOUT_KEY = "int8_weight_layout"       # "b200" (ours, FTCF_INT8_LAYOUT=0); absent: made by the reference's quant_and_save.py (=2)
+
+
+def int8_layout_of(ckpt_dir: str) -> int:
+    """ftcf_gptneox_config.int8_layout the pre-quantised files of this directory need (0: ours, 2: the reference's sm80 layout)."""
+    ini = configparser.ConfigParser()
+    ini.read(os.path.join(ckpt_dir, "config.ini"))
+    return 0 if ini["gptneox"].get(INT8_LAYOUT_KEY, "") == "b200" else 2
 
 
 def load_rank(ckpt_dir: str, tensor_para_rank: int, tensor_para_size: int, int8_mode: int = 0, enable_int8_weights: bool = False,
@@ -162,6 +179,12 @@ def load_rank(ckpt_dir: str, tensor_para_rank: int, tensor_para_size: int, int8_
         return torch.from_numpy(np.fromfile(os.path.join(ckpt_dir, f"model.{stem}.bin"), dtype=dt).reshape(shape)).to(torch.float16)
 
     preq = int8_mode == 1 and enable_int8_weights
+    if preq:
+        want = int(os.environ.get("FTCF_INT8_LAYOUT", "0"))
+        have = int8_layout_of(ckpt_dir)
+        if want != have:
+            raise ValueError(f"{ckpt_dir}: the *.q.bin files are in int8 layout {have} ({'B200, written by checkpoint.quantize_dir' if have == 0 else 'sm80 interleaved, written by the reference quant_and_save.py'})"
+                             f" but FTCF_INT8_LAYOUT selects {want}; set FTCF_INT8_LAYOUT={have}")
     fields = [("input_layernorm.bias", (h,)), ("input_layernorm.weight", (h,)),
               (None if preq else f"attention.query_key_value.weight.{r}", shapes["attention.query_key_value.weight"]),
               (f"attention.query_key_value.bias.{r}", (3 * hl,)),

@@ -32,6 +32,7 @@ std::atomic<int> g_mmha_splits{0};       // tunable "mmha_splits": force the spl
 std::atomic<int> g_mmha_onepass{1};      // tunable "mmha_onepass": one-pass (online softmax) decode attention; 0: the two-pass kernel
 std::atomic<int> g_prefill_mma{1};       // tunable "prefill_mma": tensor-core prefill attention (0: the CUDA-core kernel)
 std::atomic<int> g_mmha_prefetch{0};     // tunable "mmha_prefetch": L2 prefetch of the split's cache rows before the dependency wait
+std::atomic<int> g_mmha_lite{0};         // tunable "mmha_lite": 64-thread bulk kernel with only the K tile staged (one wave of CTAs beside the GEMMs)
 std::atomic<int> g_mmha_pdl{0};          // tunable "mmha_pdl": launch the decode attention with programmatic dependent launch   // keys per split (fp32 scores kept in shared memory)
 
 __device__ __forceinline__ float rotary_angle(int pos, int i, int rot)
@@ -531,17 +532,27 @@ __global__ void __launch_bounds__(MMHA_THREADS, 6) mmha_decode_onepass_kernel(co
 // are contiguous in the [B, H, max_len, dh] cache) BEFORE the dependency wait -- earlier positions do not depend on this
 // layer's QKV GEMM -- so every byte the launch needs is in flight at once and has usually landed when q arrives.  Scores,
 // softmax and P.V then run out of shared memory; the split partials are merged by the last arriver as in the kernels above.
-template <int DH>
-__global__ void __launch_bounds__(MMHA_THREADS, 6) mmha_decode_bulk_kernel(const MmhaP params)
+//
+// TH = 128, STAGE_V: K and V tiles in shared memory (33 KB + 5 KB static, 72 registers x 128 threads per CTA).
+// TH = 64, !STAGE_V ("lite"): only the K tile is staged (16 KB), the V rows are prefetched into L2 before the wait and read from
+// there after the softmax, the cross-group reduction buffer aliases the K tile: 17.5 KB and 64 registers x 64 threads per CTA.  Beside
+// a resident FFN2 CTA (31 K registers, 82 KB) an SM then holds 7-8 attention CTAs instead of 3, so the 680-960 CTAs of a 13B layer at
+// context 1024-1536 run as ONE wave (measured: one wave 15 us, two waves 25 us after the dependency resolves, profiles/r2_timeline_*).
+template <int DH, int TH, bool STAGE_V>
+__global__ void __launch_bounds__(TH, STAGE_V ? 6 : 16) mmha_decode_bulk_kernel(const MmhaP params)
 {
     const ftcf_mmha_params& p = params.p;
     constexpr int LPR = DH / 8;               // lanes per cache row (16 bytes each)
-    constexpr int NG = MMHA_THREADS / LPR;    // keys handled per pass
+    constexpr int NG = TH / LPR;              // keys handled per pass
     constexpr int CH = MMHA_BULK_KEYS;
+    static_assert(CH <= TH, "one softmax element per thread");
 
-    extern __shared__ __align__(128) uint8_t bulk_smem[];        // [K tile: CH x DH fp16][V tile: CH x DH fp16]
+    extern __shared__ __align__(128) uint8_t bulk_smem[];        // [K tile: CH x DH fp16][V tile: CH x DH fp16 when STAGE_V]
     __shared__ __align__(8) uint64_t bar;
-    __shared__ float s_out[NG][DH];
+    __shared__ float s_out_static[STAGE_V ? NG : 1][STAGE_V ? DH : 1];
+    // lite: the reduction buffer reuses the K tile (dead after the scores)
+    float(*s_out)[DH] = STAGE_V ? reinterpret_cast<float(*)[DH]>(&s_out_static[0][0]) : reinterpret_cast<float(*)[DH]>(bulk_smem);
+    static_assert(STAGE_V || NG * DH * 4 <= CH * DH * 2, "reduction buffer must fit the K tile");
     __shared__ float s_sc[CH];
     __shared__ float s_red[32];
     __shared__ __align__(16) __half s_q[DH];
@@ -575,15 +586,20 @@ __global__ void __launch_bounds__(MMHA_THREADS, 6) mmha_decode_bulk_kernel(const
         tma::mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t bytes = nload > 0 ? (uint32_t)nload * DH * 2 : 0u;
-        tma::mbar_arrive_expect_tx(&bar, 2 * bytes);
+        tma::mbar_arrive_expect_tx(&bar, (STAGE_V ? 2 : 1) * bytes);
         if (nload > 0) {
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tma::smem_u32(sK)),
                          "l"(kc + (size_t)start * DH), "r"(bytes), "r"(tma::smem_u32(&bar))
                          : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tma::smem_u32(sV)),
-                         "l"(vc + (size_t)start * DH), "r"(bytes), "r"(tma::smem_u32(&bar))
-                         : "memory");
+            if (STAGE_V)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tma::smem_u32(sV)),
+                             "l"(vc + (size_t)start * DH), "r"(bytes), "r"(tma::smem_u32(&bar))
+                             : "memory");
         }
+    }
+    if (!STAGE_V) {      // the V rows start travelling to L2 now (they do not depend on this layer's QKV GEMM either)
+        const char* vsrc = reinterpret_cast<const char*>(vc + (size_t)start * DH);
+        for (int off = tid * 128; off < nload * DH * 2; off += TH * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(vsrc + off));
     }
     pdl_wait();                               // qkv of this layer is complete and visible
     const unsigned long long trc_t1 = trc_now(threadIdx.x == 0);
@@ -592,7 +608,7 @@ __global__ void __launch_bounds__(MMHA_THREADS, 6) mmha_decode_bulk_kernel(const
     const __half* bias = static_cast<const __half*>(p.qkv_bias);
     const int li = tid % LPR, gi = tid / LPR;
     // ---- q (all splits), k / v (owner split): bias, rotary, append to the cache
-    for (int d = tid; d < DH; d += MMHA_THREADS) {
+    for (int d = tid; d < DH; d += TH) {
         const int rot = p.rotary_dim;
         const int pos = (*p.step - 1) - p.pad_count[b];
         const int qi = h * DH + d;
@@ -670,25 +686,54 @@ __global__ void __launch_bounds__(MMHA_THREADS, 6) mmha_decode_bulk_kernel(const
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int j = gi; j < cnt; j += NG) {
-        const float pr = s_sc[j];
-        if (pr == 0.f) continue;
-        const uint4 vv = *reinterpret_cast<const uint4*>(start + j == tlen ? &s_v[li * 8] : &sV[(size_t)j * DH + li * 8]);
-        const __half2* vh = reinterpret_cast<const __half2*>(&vv);
+    if (STAGE_V) {
+        for (int j = gi; j < cnt; j += NG) {
+            const float pr = s_sc[j];
+            if (pr == 0.f) continue;
+            const uint4 vv = *reinterpret_cast<const uint4*>(start + j == tlen ? &s_v[li * 8] : &sV[(size_t)j * DH + li * 8]);
+            const __half2* vh = reinterpret_cast<const __half2*>(&vv);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(vh[i]);
-            acc[2 * i] = fmaf(pr, f.x, acc[2 * i]);
-            acc[2 * i + 1] = fmaf(pr, f.y, acc[2 * i + 1]);
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(vh[i]);
+                acc[2 * i] = fmaf(pr, f.x, acc[2 * i]);
+                acc[2 * i + 1] = fmaf(pr, f.y, acc[2 * i + 1]);
+            }
+        }
+    } else {
+        constexpr int UNR = 8;                // V rows of one thread requested together (L2 hits after the prefetch)
+        for (int j0 = gi; j0 < cnt; j0 += NG * UNR) {
+            uint4 vv[UNR];
+            float pr[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int j = j0 + u * NG;
+                pr[u] = j < cnt ? s_sc[j] : 0.f;
+                vv[u] = make_uint4(0, 0, 0, 0);
+                if (pr[u] != 0.f) {
+                    if (start + j == tlen) vv[u] = *reinterpret_cast<const uint4*>(&s_v[li * 8]);
+                    else vv[u] = ld_stream_16(vc + (size_t)(start + j) * DH + li * 8);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const __half2* vh = reinterpret_cast<const __half2*>(&vv[u]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(vh[i]);
+                    acc[2 * i] = fmaf(pr[u], f.x, acc[2 * i]);
+                    acc[2 * i + 1] = fmaf(pr[u], f.y, acc[2 * i + 1]);
+                }
+            }
         }
     }
+    // (lite: s_out aliases the K tile -- every thread passed the barrier after the scores, nobody reads K any more)
 #pragma unroll
     for (int i = 0; i < 8; ++i) s_out[gi][li * 8 + i] = acc[i];
     __syncthreads();
 
     __half* ctx = static_cast<__half*>(p.ctx) + (size_t)b * H * DH + h * DH;
     float* part = p.partial + ((size_t)(b * H + h) * p.splits + split) * (DH + 2);
-    for (int d = tid; d < DH; d += MMHA_THREADS) {
+    for (int d = tid; d < DH; d += TH) {
         float o = 0.f;
 #pragma unroll
         for (int g = 0; g < NG; ++g) o += s_out[g][d];
@@ -722,10 +767,10 @@ __global__ void __launch_bounds__(MMHA_THREADS, 6) mmha_decode_bulk_kernel(const
     float* s_l = &s_out[0][0];
     const bool fits = nact <= CH;
     float M = -INFINITY;
-    for (int s2 = tid; s2 < nact; s2 += MMHA_THREADS) M = fmaxf(M, __ldcg(&all[s2 * (DH + 2) + DH]));
+    for (int s2 = tid; s2 < nact; s2 += TH) M = fmaxf(M, __ldcg(&all[s2 * (DH + 2) + DH]));
     M = block_max(M, s_red);
     float Lp = 0.f;
-    for (int s2 = tid; s2 < nact; s2 += MMHA_THREADS) {
+    for (int s2 = tid; s2 < nact; s2 += TH) {
         const float mi = __ldcg(&all[s2 * (DH + 2) + DH]);
         const float wgt = (mi == -INFINITY) ? 0.f : __expf(mi - M);
         if (fits) s_w[s2] = wgt;
@@ -743,7 +788,7 @@ __global__ void __launch_bounds__(MMHA_THREADS, 6) mmha_decode_bulk_kernel(const
             L = fmaf(__ldcg(&all[s2 * (DH + 2) + DH + 1]), (mi == -INFINITY) ? 0.f : __expf(mi - M), L);
         }
     }
-    for (int d = tid; d < DH; d += MMHA_THREADS) {
+    for (int d = tid; d < DH; d += TH) {
         float O0 = 0.f, O1 = 0.f, O2 = 0.f, O3 = 0.f;
         int s2 = 0;
         if (fits) {
@@ -1174,13 +1219,18 @@ extern "C" int ftcf_mmha_decode(const ftcf_mmha_params* p, void* stream)
     }
     // small batch, enough splits that no CTA gets more than 64 keys: the bulk-staged kernel
     if (mmha_bulk_applies(p->batch, p->heads, p->dh) && ceil_div(p->max_len, p->splits) <= MMHA_BULK_KEYS) {
-        const size_t smem = (size_t)2 * MMHA_BULK_KEYS * p->dh * sizeof(__half);
+        const bool lite = g_mmha_lite.load() != 0;
+        const size_t smem = (size_t)(lite ? 1 : 2) * MMHA_BULK_KEYS * p->dh * sizeof(__half);
         if (p->dh == 128) {
             static std::atomic<int> cfg128{0};
-            if (!cfg128.exchange(1)) FTCF_CUDA_CHECK(cudaFuncSetAttribute(mmha_decode_bulk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            lerr = launch_pdl(mmha_decode_bulk_kernel<128>, grid, dim3(MMHA_THREADS), smem, as_stream(stream), mp);
+            if (!cfg128.exchange(1))
+                FTCF_CUDA_CHECK(cudaFuncSetAttribute(mmha_decode_bulk_kernel<128, MMHA_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)(2 * MMHA_BULK_KEYS * 128 * sizeof(__half))));
+            lerr = lite ? launch_pdl(mmha_decode_bulk_kernel<128, 64, false>, grid, dim3(64), smem, as_stream(stream), mp)
+                        : launch_pdl(mmha_decode_bulk_kernel<128, MMHA_THREADS, true>, grid, dim3(MMHA_THREADS), smem, as_stream(stream), mp);
         } else {
-            lerr = launch_pdl(mmha_decode_bulk_kernel<64>, grid, dim3(MMHA_THREADS), smem, as_stream(stream), mp);
+            lerr = lite ? launch_pdl(mmha_decode_bulk_kernel<64, 64, false>, grid, dim3(64), smem, as_stream(stream), mp)
+                        : launch_pdl(mmha_decode_bulk_kernel<64, MMHA_THREADS, true>, grid, dim3(MMHA_THREADS), smem, as_stream(stream), mp);
         }
         FTCF_REQUIRE(lerr == cudaSuccess, FTCF_ERR_CUDA, "mmha (bulk) launch failed: %s", cudaGetErrorString(lerr));
         FTCF_LAUNCH_CHECK();

@@ -29,9 +29,10 @@
 
 namespace ftcf {
 
-std::atomic<int> g_dg_target_ctas{296};   // tunable "decode_target_ctas": CTAs a launch aims for (k-splits fill up to it)
+std::atomic<int> g_dg_target_ctas{240};   // tunable "decode_target_ctas": CTAs a launch aims for (k-splits fill up to it)
 std::atomic<int> g_dg_min_kb{8};          // tunable "decode_min_kb": fewest 128-byte K steps a k-split may get
 std::atomic<int> g_dg_evict_first{1};     // tunable "decode_evict_first"
+std::atomic<int> g_dg_lean{0};            // tunable "decode_lean": 64-register variant of the kernel (3 CTAs per SM by registers)
 std::atomic<int> g_dg_cluster{1};         // tunable "decode_cluster": k-splits of a tile as a thread-block cluster (DSMEM reduction)
 std::atomic<int> g_dg_fake_tiled{0};      // EXPERIMENT (timing only, wrong results): weight stages fetched as contiguous 16 KB runs
 std::atomic<int> g_dg_max_stages{4};      // tunable "decode_max_stages": cap on the weight-ring depth (16 KB per stage)
@@ -147,8 +148,10 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t local_addr, uint32_t ran
 
 // PRO = false: activations arrive by TMA (map_x: [m, k] fp16, box NT rows x 128 bytes, rows >= m read as zero)
 // PRO = true : activations are built in shared memory by the fused residual + LayerNorm prologue (m <= 4)
-template <int NT, bool PRO>
-__global__ void __launch_bounds__(kThreads, 2)
+// MINB = CTAs per SM the register allocation is bounded for: 2 -> up to 102 registers (90 used), 3 -> 64.  The lean variant leaves
+// room in the register file for the attention CTAs beside two resident GEMM CTAs (tunable "decode_lean").
+template <int NT, bool PRO, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const Args args)
 {
     constexpr uint32_t X_BYTES = NT * 128 * 2;            // two 64-element (128-byte) activation sub-slabs per K step
@@ -594,10 +597,10 @@ bool gemm_decode_supported(int m, int n, int k)
     return m >= 1 && m <= 32 && n >= 1 && k >= dg::BK && k % dg::BK == 0;
 }
 
-template <int NT, bool PRO>
-static int launch_decode(const CUtensorMap& mw, const CUtensorMap& mx, dg::Args a, dim3 grid, size_t smem, cudaStream_t st, bool pdl)
+template <int NT, bool PRO, int MINB>
+static int launch_decode_v(const CUtensorMap& mw, const CUtensorMap& mx, dg::Args a, dim3 grid, size_t smem, cudaStream_t st, bool pdl)
 {
-    auto kern = dg::gemm_decode_kernel<NT, PRO>;
+    auto kern = dg::gemm_decode_kernel<NT, PRO, MINB>;
     static std::atomic<size_t> configured{0};      // per instantiation; the attribute is per function (and per device context)
     if (configured.load(std::memory_order_relaxed) < smem) {
         FTCF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -629,6 +632,13 @@ static int launch_decode(const CUtensorMap& mw, const CUtensorMap& mx, dg::Args 
     FTCF_REQUIRE(err == cudaSuccess, FTCF_ERR_CUDA, "decode gemm launch failed: %s", cudaGetErrorString(err));
     FTCF_LAUNCH_CHECK();
     return FTCF_OK;
+}
+
+template <int NT, bool PRO>
+static int launch_decode(const CUtensorMap& mw, const CUtensorMap& mx, dg::Args a, dim3 grid, size_t smem, cudaStream_t st, bool pdl)
+{
+    if (g_dg_lean.load(std::memory_order_relaxed) != 0) return launch_decode_v<NT, PRO, 3>(mw, mx, a, grid, smem, st, pdl);
+    return launch_decode_v<NT, PRO, 2>(mw, mx, a, grid, smem, st, pdl);
 }
 
 // x == nullptr selects the fused-prologue variant (pro != nullptr, m <= 4)

@@ -110,3 +110,19 @@ def test_quantize_dir_writes_what_load_time_quantisation_gives(tmp_path):
         wf = wf.reshape(64 // 2, 64).float()
         exp = (wf.abs().amax(dim=0) / 128.0).half()
         assert torch.equal(s[1 * L + 0], exp)
+
+
+def test_int8_layout_marker_guards_against_the_wrong_loader_setting(tmp_path, monkeypatch):
+    """quantize_dir writes the B200 byte layout and says so in config.ini; a directory without the marker counts as made by the
+    reference's quant_and_save.py (sm80 layout).  Loading with the other FTCF_INT8_LAYOUT fails instead of producing garbage."""
+    model = _tiny_hf(True, seed=6)
+    saved = CK.convert_hf(model, str(tmp_path), 1, "fp16")
+    out = str(tmp_path / "int8")
+    CK.quantize_dir(saved, out, 1)
+    assert CK.int8_layout_of(out) == 0 and CK.int8_layout_of(saved) == 2
+    CK.read_config(out)                                               # the extra key does not disturb the config reader
+    monkeypatch.setenv("FTCF_INT8_LAYOUT", "2")
+    with pytest.raises(ValueError, match="FTCF_INT8_LAYOUT=0"):
+        CK.load_rank(out, 0, 1, int8_mode=1, enable_int8_weights=True)
+    monkeypatch.delenv("FTCF_INT8_LAYOUT")
+    CK.load_rank(out, 0, 1, int8_mode=1, enable_int8_weights=True)
