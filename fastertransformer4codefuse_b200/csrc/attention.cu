@@ -32,7 +32,7 @@ std::atomic<int> g_mmha_splits{0};       // tunable "mmha_splits": force the spl
 std::atomic<int> g_mmha_onepass{1};      // tunable "mmha_onepass": one-pass (online softmax) decode attention; 0: the two-pass kernel
 std::atomic<int> g_prefill_mma{1};       // tunable "prefill_mma": tensor-core prefill attention (0: the CUDA-core kernel)
 std::atomic<int> g_mmha_prefetch{0};     // tunable "mmha_prefetch": L2 prefetch of the split's cache rows before the dependency wait
-std::atomic<int> g_mmha_lite{0};         // tunable "mmha_lite": 64-thread bulk kernel with only the K tile staged (one wave of CTAs beside the GEMMs)
+std::atomic<int> g_mmha_lite{1};         // tunable "mmha_lite": 64-thread bulk kernel with only the K tile staged (one wave of CTAs beside the GEMMs)
 std::atomic<int> g_mmha_pdl{0};          // tunable "mmha_pdl": launch the decode attention with programmatic dependent launch   // keys per split (fp32 scores kept in shared memory)
 
 __device__ __forceinline__ float rotary_angle(int pos, int i, int rot)
@@ -760,12 +760,12 @@ __global__ void __launch_bounds__(TH, STAGE_V ? 6 : 16) mmha_decode_bulk_kernel(
         return;
     }
     __threadfence();
-    // merge of the nact partials (fixed order): the per-split weights exp(m_s - M) go to shared memory once, then every thread
-    // sums its dimension with independent loads, four in flight (the naive loop chained ~3 * nact dependent L2 round trips)
+    // Merge of the nact partials by the last arriver, in two load rounds instead of a chain of them (it is the tail of the layer's
+    // critical path: 6 us before, under the FFN2 weight stream every dependent round costs 2-3 us): round 1 fetches every
+    // split's (max, sum) at once -> weights exp(m_s - M) in shared memory and the normaliser (fixed reduction tree: the result
+    // does not depend on arrival order); round 2 requests up to 24 partial rows per dimension before the first is used.
     const float* all = p.partial + (size_t)(b * H + h) * p.splits * (DH + 2);
-    float* s_w = s_sc;                        // nact <= grid.z weights; s_sc holds CH floats, larger merges fall back to s_out
-    float* s_l = &s_out[0][0];
-    const bool fits = nact <= CH;
+    float* s_w = reinterpret_cast<float*>(&s_out[0][0]);      // nact weights (nact <= max_len / 64 <= NG * DH)
     float M = -INFINITY;
     for (int s2 = tid; s2 < nact; s2 += TH) M = fmaxf(M, __ldcg(&all[s2 * (DH + 2) + DH]));
     M = block_max(M, s_red);
@@ -773,55 +773,25 @@ __global__ void __launch_bounds__(TH, STAGE_V ? 6 : 16) mmha_decode_bulk_kernel(
     for (int s2 = tid; s2 < nact; s2 += TH) {
         const float mi = __ldcg(&all[s2 * (DH + 2) + DH]);
         const float wgt = (mi == -INFINITY) ? 0.f : __expf(mi - M);
-        if (fits) s_w[s2] = wgt;
+        s_w[s2] = wgt;
         Lp = fmaf(__ldcg(&all[s2 * (DH + 2) + DH + 1]), wgt, Lp);
     }
-    (void)s_l;
-    // the normaliser is summed in split order by one thread so that it does not depend on the reduction tree
+    const float L = block_sum(Lp, s_red);
     __syncthreads();
-    float L = 0.f;
-    if (fits) {
-        for (int s2 = 0; s2 < nact; ++s2) L = fmaf(__ldcg(&all[s2 * (DH + 2) + DH + 1]), s_w[s2], L);
-    } else {
-        for (int s2 = 0; s2 < nact; ++s2) {
-            const float mi = __ldcg(&all[s2 * (DH + 2) + DH]);
-            L = fmaf(__ldcg(&all[s2 * (DH + 2) + DH + 1]), (mi == -INFINITY) ? 0.f : __expf(mi - M), L);
-        }
-    }
+    constexpr int MB = 24;
     for (int d = tid; d < DH; d += TH) {
         float O0 = 0.f, O1 = 0.f, O2 = 0.f, O3 = 0.f;
-        int s2 = 0;
-        if (fits) {
-            for (; s2 + 8 <= nact; s2 += 8) {        // eight partial rows requested before the first is used
-                float a[8];
+        for (int s0 = 0; s0 < nact; s0 += MB) {
+            float a[MB];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) a[u] = __ldcg(&all[(s2 + u) * (DH + 2) + d]);
+            for (int u = 0; u < MB; ++u) a[u] = (s0 + u < nact) ? __ldcg(&all[(s0 + u) * (DH + 2) + d]) : 0.f;
 #pragma unroll
-                for (int u = 0; u < 8; u += 4) {
-                    O0 = fmaf(a[u], s_w[s2 + u], O0);
-                    O1 = fmaf(a[u + 1], s_w[s2 + u + 1], O1);
-                    O2 = fmaf(a[u + 2], s_w[s2 + u + 2], O2);
-                    O3 = fmaf(a[u + 3], s_w[s2 + u + 3], O3);
-                }
+            for (int u = 0; u < MB; u += 4) {
+                O0 = fmaf(a[u], (s0 + u < nact) ? s_w[s0 + u] : 0.f, O0);
+                O1 = fmaf(a[u + 1], (s0 + u + 1 < nact) ? s_w[s0 + u + 1] : 0.f, O1);
+                O2 = fmaf(a[u + 2], (s0 + u + 2 < nact) ? s_w[s0 + u + 2] : 0.f, O2);
+                O3 = fmaf(a[u + 3], (s0 + u + 3 < nact) ? s_w[s0 + u + 3] : 0.f, O3);
             }
-            for (; s2 + 4 <= nact; s2 += 4) {
-                const float a0 = __ldcg(&all[(s2 + 0) * (DH + 2) + d]), a1 = __ldcg(&all[(s2 + 1) * (DH + 2) + d]);
-                const float a2 = __ldcg(&all[(s2 + 2) * (DH + 2) + d]), a3 = __ldcg(&all[(s2 + 3) * (DH + 2) + d]);
-                O0 = fmaf(a0, s_w[s2], O0);
-                O1 = fmaf(a1, s_w[s2 + 1], O1);
-                O2 = fmaf(a2, s_w[s2 + 2], O2);
-                O3 = fmaf(a3, s_w[s2 + 3], O3);
-            }
-        }
-        for (; s2 < nact; ++s2) {
-            float wgt;
-            if (fits) {
-                wgt = s_w[s2];
-            } else {
-                const float mi = __ldcg(&all[s2 * (DH + 2) + DH]);
-                wgt = (mi == -INFINITY) ? 0.f : __expf(mi - M);
-            }
-            O0 = fmaf(__ldcg(&all[s2 * (DH + 2) + d]), wgt, O0);
         }
         ctx[d] = __float2half_rn(((O0 + O1) + (O2 + O3)) * (1.f / (L + 1e-6f)));
     }
@@ -1219,7 +1189,8 @@ extern "C" int ftcf_mmha_decode(const ftcf_mmha_params* p, void* stream)
     }
     // small batch, enough splits that no CTA gets more than 64 keys: the bulk-staged kernel
     if (mmha_bulk_applies(p->batch, p->heads, p->dh) && ceil_div(p->max_len, p->splits) <= MMHA_BULK_KEYS) {
-        const bool lite = g_mmha_lite.load() != 0;
+        // measured in the 13B step (profiles/r2_decode_experiments.txt): batch 1 -2.3 %, batch 2 +0.6 % -> one sequence's heads only
+        const bool lite = g_mmha_lite.load() != 0 && p->batch * p->heads <= 48;
         const size_t smem = (size_t)(lite ? 1 : 2) * MMHA_BULK_KEYS * p->dh * sizeof(__half);
         if (p->dh == 128) {
             static std::atomic<int> cfg128{0};
