@@ -43,7 +43,7 @@ int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, con
                       const SkPro* pro, cudaStream_t st, const ftcf_tp_exchange* push = nullptr, int push_kind = 0, int push_layer = 0,
                       const ftcf_launch_hint* hint = nullptr);
 bool gemm_decode_supported(int m, int n, int k);
-extern std::atomic<int> g_dg_target_ctas, g_dg_min_kb, g_dg_evict_first, g_dg_max_stages, g_dg_fake_tiled, g_dg_cluster, g_dg_lean;
+extern std::atomic<int> g_dg_target_ctas, g_dg_min_kb, g_dg_evict_first, g_dg_max_stages, g_dg_cluster, g_dg_lean;
 std::atomic<int> g_decode_impl{3};   // tunable "decode_impl": 3 = tcgen05 decode GEMM for int8 at m <= 32 (default), 1 = round-1 streaming mma.sync kernel
 extern std::atomic<int> g_prefill_mma, g_mmha_onepass, g_mmha_splits, g_mmha_bulk, g_mmha_lite;
 extern std::atomic<int> g_mmha_pdl, g_mmha_prefetch, g_sk_carveout, g_sk_evict_first, g_tc_ksplit, g_sk_target_ctas;
@@ -78,7 +78,6 @@ extern "C" int ftcf_set_tunable(const char* name, int value)
     else if (n == "decode_evict_first") g_dg_evict_first.store(value);
     else if (n == "decode_impl") g_decode_impl.store(value);
     else if (n == "decode_max_stages") g_dg_max_stages.store(value);
-    else if (n == "decode_fake_tiled") g_dg_fake_tiled.store(value);
     else if (n == "decode_cluster") g_dg_cluster.store(value);
     else if (n == "decode_lean") g_dg_lean.store(value);
     else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_tunable: unknown tunable %s", name);

@@ -164,7 +164,7 @@ struct ftcf_gptneox {
     cudaStream_t caller_stream = nullptr;   // the stream handed in at construction (torch's current stream, GptNeoXOp.h:180)
     cudaEvent_t caller_ev = nullptr;
     cudaStream_t side = nullptr;            // second branch of the decode layer (FFN) so that it overlaps the attention branch
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_attn = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t side2 = nullptr;           // KV-cache L2 prefetch of the decode layer
     cudaEvent_t ev_join2 = nullptr;
     int h = 0, Hl = 0, hl = 0, inter_l = 0, Vp = 0, Vl = 0, t = 1, rank = 0;
@@ -185,7 +185,7 @@ struct ftcf_gptneox {
     int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_kv_prefetch = 0, opt_pro_ctas = 148, opt_tp_fused = 1;
     // CTA targets of the four decode GEMMs of a layer in the fused path (0: pro_ctas for QKV / FFN1, the kernel's default for O / FFN2)
     int opt_qkv_ctas = 0, opt_ffn1_ctas = 0, opt_o_ctas = 0, opt_ffn2_ctas = 160,   // FFN2 at one CTA per SM leaves the attention kernel its slots (profiles/r2_decode_experiments.txt)
-         opt_ffn2_no_pdl = 0, opt_ffn2_stages = 0, opt_o_stages = 0, opt_ffn2_after_attn = 0, opt_qkv_first = 0;
+         opt_ffn2_no_pdl = 0, opt_ffn2_stages = 0, opt_o_stages = 0;
 
     // request-sized buffers (grow only)
     DevBuf kv, x, x2, n1, n2, qkv, qbuf, ctx, attn, inter, ffn, logits, logits_local, logits_gather, samp_ws, small, mmha_part,
@@ -435,7 +435,6 @@ extern "C" int ftcf_gptneox_create(ftcf_gptneox** out, const ftcf_gptneox_config
         cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_attn, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithPriority(&e->side2, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
         set_error("create: cannot create the engine stream");
@@ -555,7 +554,6 @@ extern "C" void ftcf_gptneox_destroy(ftcf_gptneox* e)
     if (e->caller_ev) cudaEventDestroy(e->caller_ev);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
-    if (e->ev_attn) cudaEventDestroy(e->ev_attn);
     if (e->ev_join2) cudaEventDestroy(e->ev_join2);
     if (e->side2) cudaStreamDestroy(e->side2);
     if (e->side) { splitk_release_for_stream(e->side); cudaStreamDestroy(e->side); }
@@ -582,8 +580,6 @@ extern "C" int ftcf_gptneox_set_option(ftcf_gptneox* e, const char* name, int va
     else if (n == "ffn2_no_pdl") e->opt_ffn2_no_pdl = value;
     else if (n == "ffn2_stages") e->opt_ffn2_stages = value;
     else if (n == "o_stages") e->opt_o_stages = value;
-    else if (n == "ffn2_after_attn") e->opt_ffn2_after_attn = value;
-    else if (n == "qkv_first") e->opt_qkv_first = value;
     else FTCF_REQUIRE(false, FTCF_ERR_INVALID, "set_option: unknown option %s", name);
     e->drop_graphs();   // anything captured may be stale
     return FTCF_OK;
@@ -712,36 +708,14 @@ int decode_step(ftcf_gptneox* e, const Small& s, const ftcf_sampling_params& sp,
                 if (w8) return ftcf_gemm_w8a16_ex(e->ctx.p, static_cast<const uint8_t*>(lw.w[1]), lw.scale[1], nullptr, attn[l & 1], B, e->h, e->hl, 0, e->opt_gemm_impl, &ho, st);
                 return ftcf_gemm_f16(e->ctx.p, lw.w[1], nullptr, attn[l & 1], B, e->h, e->hl, e->h, 0, 0, 1, st);
             };
-            if (e->opt_two_branch && e->opt_qkv_first) {
-                // QKV runs alone first (it heads the layer's longest dependency chain QKV -> attention -> O); the FFN branch starts
-                // when it is done and streams its 210 MB beside the attention chain, which is light on HBM but long on latency
-                FTCF_TRY(qkv());
-                FTCF_CUDA_CHECK(cudaEventRecord(e->ev_attn, st));
-                FTCF_CUDA_CHECK(cudaStreamWaitEvent(sb, e->ev_attn, 0));
-                FTCF_TRY(ffn1());
-                FTCF_TRY(ffn2());
-                FTCF_CUDA_CHECK(cudaEventRecord(e->ev_join, sb));
-                FTCF_TRY(ftcf_mmha_decode(&mp, st));
-                FTCF_TRY(oproj());
-            } else if (e->opt_two_branch && e->opt_ffn2_after_attn) {
-                // FFN2 is held back until the attention kernel has finished: the attention (on the layer's critical path
-                // QKV -> attention -> O) then has the SMs and HBM to itself instead of queueing behind FFN2's CTAs
-                FTCF_TRY(ffn1());
-                FTCF_TRY(qkv());
-                FTCF_TRY(ftcf_mmha_decode(&mp, st));
-                FTCF_CUDA_CHECK(cudaEventRecord(e->ev_attn, st));
-                FTCF_CUDA_CHECK(cudaStreamWaitEvent(sb, e->ev_attn, 0));
-                FTCF_TRY(ffn2());
-                FTCF_CUDA_CHECK(cudaEventRecord(e->ev_join, sb));
-                FTCF_TRY(oproj());
-            } else {
-                FTCF_TRY(ffn1());
-                FTCF_TRY(ffn2());
-                if (e->opt_two_branch) FTCF_CUDA_CHECK(cudaEventRecord(e->ev_join, sb));
-                FTCF_TRY(qkv());
-                FTCF_TRY(ftcf_mmha_decode(&mp, st));
-                FTCF_TRY(oproj());
-            }
+            // (measured and removed: QKV alone first, then FFN beside the attention: +25 % per token; FFN2 held back until the
+            // attention finished: +4 %; profiles/r2_decode_experiments.txt)
+            FTCF_TRY(ffn1());
+            FTCF_TRY(ffn2());
+            if (e->opt_two_branch) FTCF_CUDA_CHECK(cudaEventRecord(e->ev_join, sb));
+            FTCF_TRY(qkv());
+            FTCF_TRY(ftcf_mmha_decode(&mp, st));
+            FTCF_TRY(oproj());
             if (e->opt_two_branch) FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join, 0));
             if (kvpf) FTCF_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join2, 0));
         }

@@ -34,7 +34,6 @@ std::atomic<int> g_dg_min_kb{8};          // tunable "decode_min_kb": fewest 128
 std::atomic<int> g_dg_evict_first{1};     // tunable "decode_evict_first"
 std::atomic<int> g_dg_lean{0};            // tunable "decode_lean": 64-register variant of the kernel (3 CTAs per SM by registers)
 std::atomic<int> g_dg_cluster{1};         // tunable "decode_cluster": k-splits of a tile as a thread-block cluster (DSMEM reduction)
-std::atomic<int> g_dg_fake_tiled{0};      // EXPERIMENT (timing only, wrong results): weight stages fetched as contiguous 16 KB runs
 std::atomic<int> g_dg_max_stages{4};      // tunable "decode_max_stages": cap on the weight-ring depth (16 KB per stage)
 
 // ---- split-K scratch: one (partials, tickets) slot per STREAM.  Launches on one stream are ordered (a PDL-launched successor
@@ -117,8 +116,6 @@ struct Args {
     int* tickets;     // one self-resetting counter per feature tile
     int stages;       // depth of the weight ring (<= kMaxStages)
     int evict_first;
-    int fake_tiled;
-    const uint8_t* w_raw;
     SkPro pro;        // PRO only
     ftcf_tp_exchange push;   // push.tp > 1: the epilogue stores the output into every rank's exchange area instead of y
     int push_kind, push_layer;
@@ -195,11 +192,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     // role in warp-uniform control flow (tma::elect_one_sync), never from behind `if (lane == 0)`.
     auto load_w = [&](int kb, int s) {
         uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-        if (args.fake_tiled) {
-            const uint8_t* src = args.w_raw + ((size_t)blockIdx.x * kb_all + kb0 + kb) * W_BYTES;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(st)),
-                         "l"(src), "r"(W_BYTES), "r"(smem_u32(&bar_full[s])) : "memory");
-        } else if (args.evict_first) {
+        if (args.evict_first) {
             tma::load_2d_hint(st, &map_w, &bar_full[s], (kb0 + kb) * BK, n0, tma::l2_policy_evict_first());
         } else {
             tma::load_2d(st, &map_w, &bar_full[s], (kb0 + kb) * BK, n0);
@@ -665,8 +658,6 @@ int gemm_w8a16_decode(const void* x, const uint8_t* w_nk, const void* scale, con
     a.y = static_cast<__half*>(y);
     a.m = m; a.n = n; a.k = k; a.ldy = n; a.act = act;
     a.evict_first = g_dg_evict_first.load(std::memory_order_relaxed);
-    a.fake_tiled = (n % 128 == 0) ? g_dg_fake_tiled.load(std::memory_order_relaxed) : 0;
-    a.w_raw = w_nk;
     if (push != nullptr) {
         FTCF_REQUIRE(push->tp > 1 && push->tp <= 8 && push->rank >= 0 && push->rank < push->tp && m <= push->m_max && n == push->h &&
                          (push_kind == 0 || push_kind == 1) && push->step != nullptr,
