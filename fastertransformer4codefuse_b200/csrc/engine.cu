@@ -182,7 +182,7 @@ struct ftcf_gptneox {
     static constexpr int kTpMaxRows = 32;
 
     // options
-    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_kv_prefetch = 0, opt_pro_ctas = 148, opt_tp_fused = 1;
+    int opt_cuda_graph = 1, opt_gemm_impl = 0, opt_step_timing = 0, opt_two_branch = 1, opt_fused_ln = 1, opt_kv_prefetch = 0, opt_pro_ctas = 148, opt_tp_fused = 1, opt_layer_hints = 1;
     // CTA targets of the four decode GEMMs of a layer in the fused path (0: pro_ctas for QKV / FFN1, the kernel's default for O / FFN2)
     int opt_qkv_ctas = 0, opt_ffn1_ctas = 0, opt_o_ctas = 0, opt_ffn2_ctas = 160,   // FFN2 at one CTA per SM leaves the attention kernel its slots (profiles/r2_decode_experiments.txt)
          opt_ffn2_no_pdl = 0, opt_ffn2_stages = 0, opt_o_stages = 0;
@@ -230,11 +230,15 @@ struct Small {   // carved out of one small device slab; all int32 / float / u8 
     void* curand;
 };
 
-int engine_gemm(ftcf_gptneox* e, cudaStream_t st, const void* x, int layer, int kind, const __half* bias, void* y, int m, int n, int k, int act)
+int engine_gemm(ftcf_gptneox* e, cudaStream_t st, const void* x, int layer, int kind, const __half* bias, void* y, int m, int n, int k, int act,
+                int target_ctas = 0)
 {
     const LayerW& L = e->layers[layer];
-    if (e->cfg.int8_mode == 1)
-        return ftcf_gemm_w8a16(x, static_cast<const uint8_t*>(L.w[kind]), L.scale[kind], bias, y, m, n, k, act, e->opt_gemm_impl, st);
+    if (e->cfg.int8_mode == 1) {
+        const ftcf_launch_hint hint{target_ctas, 0, 0};
+        return ftcf_gemm_w8a16_ex(x, static_cast<const uint8_t*>(L.w[kind]), L.scale[kind], bias, y, m, n, k, act, e->opt_gemm_impl,
+                                  target_ctas > 0 ? &hint : nullptr, st);
+    }
     return ftcf_gemm_f16(x, L.w[kind], bias, y, m, n, k, n, act, 0, e->opt_gemm_impl, st);
 }
 
@@ -328,6 +332,9 @@ int run_layer(ftcf_gptneox* e, int l, int m, AttnFn&& attn_fn, bool tp_decode = 
         }
         // decode with m <= 4 rows (tensor parallel, or fused_ln = 2): the two LayerNorms run as the prologue of the GEMMs that
         // consume them (the residual add cannot: with t > 1 its sum goes through the all-reduce first)
+        // the two GEMMs that start the branches share the CTA slots (2 per SM) instead of queueing behind each other: at batch 32 the
+        // QKV GEMM -- head of the critical path QKV -> attention -> O -- otherwise ends 30 us after FFN1 (profiles/r2_timeline_b32.txt)
+        const int share = (fork && e->opt_layer_hints != 0) ? e->opt_pro_ctas : 0;
         const bool ln_pro = e->opt_fused_ln != 0 && m <= 4 && e->h % 128 == 0 && e->h <= 16384 && (e->t > 1 || e->opt_fused_ln == 2);
         auto ln_gemm = [&](cudaStream_t s2, const __half* g, const __half* b, int kind, const __half* bias, void* y, int n, int act) -> int {
             ftcf_ln_prologue pro{};
@@ -341,19 +348,19 @@ int run_layer(ftcf_gptneox* e, int l, int m, AttnFn&& attn_fn, bool tp_decode = 
             FTCF_TRY(ln_gemm(sb, L.ln2_g, L.ln2_b, 2, L.ffn1_b, e->inter.p, e->inter_l, 1));
         } else {
             FTCF_TRY(ftcf_layernorm(x, L.ln2_g, L.ln2_b, e->n2.p, m, e->h, c.layernorm_eps, sb));
-            FTCF_TRY(engine_gemm(e, sb, e->n2.p, l, 2, L.ffn1_b, e->inter.p, m, e->inter_l, e->h, 1));
+            FTCF_TRY(engine_gemm(e, sb, e->n2.p, l, 2, L.ffn1_b, e->inter.p, m, e->inter_l, e->h, 1, share));
         }
         // decode rows with the exchange area up: the O / FFN2 epilogues store their tiles into every rank's area and
         // ftcf_tp_gather_residual rebuilds the all-reduced residual (no residual kernel, no ncclAllReduce)
         const bool tp_push = tp_decode && e->tp_fused && e->opt_tp_fused != 0 && c.int8_mode == 1 && m <= ftcf_gptneox::kTpMaxRows;
         if (tp_push) FTCF_TRY(ftcf_gemm_w8a16_tp_push(e->inter.p, static_cast<const uint8_t*>(L.w[3]), L.scale[3], &e->tpx, 1, l, m, e->h, e->inter_l, nullptr, sb));
-        else FTCF_TRY(engine_gemm(e, sb, e->inter.p, l, 3, nullptr, e->ffn.p, m, e->h, e->inter_l, 0));
+        else FTCF_TRY(engine_gemm(e, sb, e->inter.p, l, 3, nullptr, e->ffn.p, m, e->h, e->inter_l, 0, share > 0 ? e->opt_ffn2_ctas : 0));
         if (fork) FTCF_CUDA_CHECK(cudaEventRecord(e->ev_join, sb));
         if (ln_pro) {
             FTCF_TRY(ln_gemm(st, L.ln1_g, L.ln1_b, 0, nullptr, e->qkv.p, 3 * e->hl, 0));
         } else {
             FTCF_TRY(ftcf_layernorm(x, L.ln1_g, L.ln1_b, e->n1.p, m, e->h, c.layernorm_eps, st));
-            FTCF_TRY(engine_gemm(e, st, e->n1.p, l, 0, nullptr, e->qkv.p, m, 3 * e->hl, e->h, 0));
+            FTCF_TRY(engine_gemm(e, st, e->n1.p, l, 0, nullptr, e->qkv.p, m, 3 * e->hl, e->h, 0, share));
         }
         FTCF_TRY(attn_fn(l));
         if (tp_push) FTCF_TRY(ftcf_gemm_w8a16_tp_push(e->ctx.p, static_cast<const uint8_t*>(L.w[1]), L.scale[1], &e->tpx, 0, l, m, e->h, e->hl, nullptr, st));
@@ -573,6 +580,7 @@ extern "C" int ftcf_gptneox_set_option(ftcf_gptneox* e, const char* name, int va
     else if (n == "kv_prefetch") e->opt_kv_prefetch = value;
     else if (n == "pro_ctas") e->opt_pro_ctas = value;
     else if (n == "tp_fused") e->opt_tp_fused = value;
+    else if (n == "layer_hints") e->opt_layer_hints = value;
     else if (n == "qkv_ctas") e->opt_qkv_ctas = value;
     else if (n == "ffn1_ctas") e->opt_ffn1_ctas = value;
     else if (n == "o_ctas") e->opt_o_ctas = value;
