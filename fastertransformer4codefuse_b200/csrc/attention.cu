@@ -1189,8 +1189,10 @@ extern "C" int ftcf_mmha_decode(const ftcf_mmha_params* p, void* stream)
     }
     // small batch, enough splits that no CTA gets more than 64 keys: the bulk-staged kernel
     if (mmha_bulk_applies(p->batch, p->heads, p->dh) && ceil_div(p->max_len, p->splits) <= MMHA_BULK_KEYS) {
-        // measured in the 13B step (profiles/r2_decode_experiments.txt): batch 1 -2.3 %, batch 2 +0.6 % -> one sequence's heads only
-        const bool lite = g_mmha_lite.load() != 0 && p->batch * p->heads <= 48;
+        // The small CTAs pay off only where the 128-thread kernel would need more than one wave beside the GEMMs (~440 CTAs).
+        // Measured in the 13B step (profiles/r2_decode_experiments.txt): one GPU, batch 1 (960 CTAs) -2.3 %; batch 2 +0.6 %;
+        // two GPUs, batch 1 (480 CTAs) +5 %.
+        const bool lite = g_mmha_lite.load() != 0 && p->batch * p->heads <= 48 && (long long)p->batch * p->heads * p->splits > 600;
         const size_t smem = (size_t)(lite ? 1 : 2) * MMHA_BULK_KEYS * p->dh * sizeof(__half);
         if (p->dh == 128) {
             static std::atomic<int> cfg128{0};
