@@ -81,6 +81,18 @@ for int8_mode in (1, 0):
             exp = ref.forward(ids2, lens2, 10)
             report(f"int8={int8_mode} parallel_residual={gptj} second ragged request on the cached graph",
                    np.array_equal(got, exp["output_ids"]) and np.array_equal(got_len, exp["sequence_lengths"]))
+        if int8_mode == 1 and gptj:
+            # more than 4 rows: the decode step leaves the fused path (run_layer: push GEMMs with global split-K partials + stand-alone
+            # gather, CTA-share hints) -- batch 6, ragged
+            lens6 = [11, 6, 9, 3, 10, 8]
+            ids6 = prompts(cfg, lens6, 11, 7)
+            for graph in (0, 1):
+                op.set_option("cuda_graph", graph)
+                got, got_len = run(op, ids6, lens6, 8)
+                if rank == 0:
+                    exp = ref.forward(ids6, lens6, 8)
+                    report(f"int8=1 parallel_residual=True batch 6 graph={graph}",
+                           np.array_equal(got, exp["output_ids"]) and np.array_equal(got_len, exp["sequence_lengths"]))
         del op
 
 # ---- every row finishes early: end_id := the third token the oracle generates for a single-row request
