@@ -1131,7 +1131,9 @@ using namespace ftcf;
 
 static bool mmha_bulk_applies(int batch, int heads, int dh)
 {
-    return g_mmha_bulk.load() != 0 && batch * heads <= 320 && (dh == 64 || dh == 128);
+    // small BATCH, not just few (row, head) pairs: with tensor parallelism a batch of 32 has only 160-320 pairs per rank, but it is
+    // a bandwidth problem (hundreds of MB of cache per layer) that belongs to the streaming kernels below
+    return g_mmha_bulk.load() != 0 && batch <= 8 && batch * heads <= 320 && (dh == 64 || dh == 128);
 }
 
 extern "C" int ftcf_mmha_choose_splits(int batch, int heads, int max_len)
