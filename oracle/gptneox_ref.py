@@ -23,18 +23,22 @@ Follows (paths relative to /root/reference/src/fastertransformer):
                           (u8 -> fp16, times scale IN fp16, then mma with fp32 accumulate)
   * weight list order     th_op/gptneox/GptNeoXOp.h:121-174, examples/pytorch/codefuse/codefuse_example.py:182-419
   * sampling              oracle/sampling_ref.py
+  * beam search           oracle/beam_search_ref.py (forward_beam below: tiling, cache indirection, gatherTree with parents)
 
 Parity status.  The reference as a whole cannot be built or run for this path on this image or on sm_100 (SURVEY.md
 section 8c), but its kernels can: oracle/Makefile compiles the reference's own .cu files (LayerNorm, residual add, decode
-attention, top-k sampling, penalties) for sm_100a into oracle/_ref/libref_kernels.so, and tests/test_ref_kernels_gpu.py
-runs them on the B200 beside our kernels AND beside this restatement.  Pinned that way: LayerNorm (bit-level: > 97 % of
-the elements identical, the rest one fp16 ulp from the fp32 reduction order), the parallel-residual add (bit-exact), the
-decode attention incl. bias + NeoX rotary + cache append (fp16 tolerance stated in the test), the sampling chain (token
-ids / finished flags / lengths identical over multi-step seeded runs).  The quantiser is pinned by the reference's
-object code on the CPU (oracle/_ref/libref_quant.so) and its KATs; the model wiring by HuggingFace GPTNeoXForCausalLM
-goldens (tests/golden/, tests/golden/make_golden.py).  Still PARITY UNPINNED by the reference: the INT8 GEMM rounding
-(its CUTLASS kernel refuses sm >= 90) and the prefill bias + rotary + split kernel (open item); the
-prefill softmax chain and the output gather are pinned (tests/test_ref_kernels_prefill_gpu.py).
+attention, prefill bias + rotary + split, masked softmax, top-k / top-p sampling, penalties, stop criteria, beam-search
+penalties + softmax/top-k, gatherTree) for sm_100a into oracle/_ref/libref_kernels.so, and tests/test_ref_kernels*_gpu.py,
+tests/test_beam_search_gpu.py run them on the B200 beside our kernels AND beside this restatement.  Pinned that way: LayerNorm
+(bit-level: > 97 % of the elements identical, the rest one fp16 ulp from the fp32 reduction order), the parallel-residual add
+(bit-exact), the decode attention incl. bias + NeoX rotary + cache append (fp16 tolerance stated in the test), the prefill
+bias + rotary + split, the prefill softmax chain, the sampling chain and the beam search (token ids / parents / finished flags /
+lengths identical over multi-step seeded runs), the output gather with and without parents.  The quantiser is pinned by the
+reference's object code on the CPU (oracle/_ref/libref_quant.so) and its KATs; the model wiring by HuggingFace
+GPTNeoXForCausalLM goldens (tests/golden/, tests/golden/make_golden.py); the request loop as a whole by the reference's
+UNCHANGED driver (oracle/_ref/codefuse_example.compiled, tests/test_driver_gpu.py).  Still PARITY UNPINNED by the reference:
+only the INT8 GEMM rounding (its CUTLASS kernel refuses sm >= 90); it is held by the exact dequant round trip and the
+reference's own tolerance (rtol 1e-3 / atol 2e-3) instead.
 
 Tensor parallelism is emulated: `ranks` weight sets are evaluated one after the
 other and summed where the reference all-reduces.

@@ -52,6 +52,34 @@ def test_bad_arguments_are_reported():
     assert lib.ftcf_mmha_decode(None, None) == 1
 
 
+def test_host_side_sizing_and_kernel_choice():
+    """Pure host logic of the C ABI (no launch): decode-attention split choice and the kernel family it implies, beam-search
+    workspace sizing, beam-search argument checks."""
+    lib = capi.load()
+    # batch 1, 13B heads: the bulk-staged kernel, one CTA per 64 keys; it publishes nothing at larger batches
+    assert lib.ftcf_mmha_choose_splits(1, 40, 1536) == 24
+    assert lib.ftcf_mmha_choose_splits(4, 40, 1536) == 24
+    # batch 32 (and tensor-parallel ranks at batch 32, 5-20 heads each): the streaming kernels, at least 128 keys per split
+    for heads in (40, 20, 10, 5):
+        s = lib.ftcf_mmha_choose_splits(32, heads, 2560)
+        assert 1 <= s <= 2560 // 128, (heads, s)
+    assert lib.ftcf_mmha_choose_splits(32, 40, 2560) == 1
+    # a split never gets more keys than the score buffer holds (4096)
+    assert lib.ftcf_mmha_choose_splits(64, 40, 32768) >= 8
+    # beam-search workspace: grows with rows, beams and history length; zero for nonsense
+    a = lib.ftcf_beam_workspace_bytes(1, 3, 100864, 1536)
+    assert a > 0 and lib.ftcf_beam_workspace_bytes(2, 3, 100864, 1536) > a and lib.ftcf_beam_workspace_bytes(1, 8, 100864, 1536) > a
+    assert lib.ftcf_beam_workspace_bytes(1, 3, 100864, 4096) > a
+    assert lib.ftcf_beam_workspace_bytes(0, 3, 100864, 1536) == 0
+    assert lib.ftcf_beam_search_step(None, None) == 1                                     # FTCF_ERR_INVALID
+    bp = capi.BeamParams()
+    bp.batch, bp.beam_width, bp.vocab, bp.vocab_padded, bp.max_len = 1, 33, 100, 100, 10
+    assert lib.ftcf_beam_search_step(bp, None) != 0 and b"beam_width" in lib.ftcf_last_error()
+    bp.beam_width = 1
+    assert lib.ftcf_beam_search_step(bp, None) == 1                                       # beam search needs beam_width > 1
+    assert lib.ftcf_gather_output_beams(None, None, None, None, None, None, 1, 3, 4, 8, 0, None) == 1
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(64, 48), (2, 32, 16), (128, 200)])
 def test_libth_common_quantiser_vs_oracle(dtype, shape):
