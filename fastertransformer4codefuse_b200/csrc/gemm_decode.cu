@@ -17,8 +17,13 @@
 //     W never exists in shared memory;
 //   * warp 1: one thread issues tcgen05.mma.kind::f16 (TS form, M128 x N x K16, fp32 accumulators in TMEM), tcgen05.commit hands
 //     the A stage and the activation slab back;
-//   * epilogue from tcgen05.ld: per-feature dequant scale (fp32), bias, tanh-GELU, fp16 store; split-K partials are fp32 in a
-//     per-stream scratch, summed in a fixed order by the last CTA of a tile (ticket) -- deterministic;
+//   * epilogue from tcgen05.ld: per-feature dequant scale (fp32), bias, tanh-GELU, fp16 store -- or, with tensor parallelism,
+//     8-byte flagged stores of the tile into every rank's exchange area (ftcf_tp_exchange: the all-reduce of the layer);
+//   * k-splits of a tile: a thread-block cluster whose members add their accumulators into the leader's shared memory over
+//     DSMEM in rank order (when the buffer is <= 16 KB), else fp32 partials in a per-stream scratch summed in a fixed order by
+//     the last CTA of the tile (ticket) -- both deterministic; never more CTAs than co-resident slots;
+//   * single-thread instructions (TMA, tcgen05.mma, tcgen05.commit) are issued by the lane `elect.sync` picks, from warp-uniform
+//     control flow: behind `if (lane == 0)` the compiler serialises them per lane (118 vs 25 cycles per MMA, tools/umma_probe.cu);
 //   * optional fused prologue (m <= 4): previous layer's residual add + LayerNorm computed by every CTA into shared memory
 //     (common.cuh, SkPro), from which the converter warps build the swizzled activation slab of each K step.
 #include <algorithm>
