@@ -83,3 +83,33 @@ def test_oracle_repetition_penalty_walks_the_beam_history():
     for j in range(K):
         hist = {int(run.ids[step - 1, j])} | {int(t) for t in run.ids0[:max_in, 0]}
         assert {int(i) for i in np.nonzero(x[j] == 0.5)[0]} == hist
+
+
+def test_oracle_forward_beam_output_contract():
+    """Model-level restatement (GptNeoXRef.forward_beam): output shapes and the gatherTree contract on a ragged batch -- every beam
+    starts with its request's prompt, the pad gap is gone, sequence_lengths counts max_input_length + generated (pad gap NOT
+    subtracted, as for sampling), cum_log_probs come out best first, and deciding on the run's own traced logits reproduces it."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fastertransformer4codefuse_b200 import weights as W
+    from helpers import oracle_from_rank_weights, tiny_cfg
+    cfg = tiny_cfg()
+    rw = W.make_synthetic(cfg, 1, 0, 1, "cpu", seed=21, keep_plain=True)
+    ref = oracle_from_rank_weights(cfg, [rw], 1)
+    g = np.random.default_rng(12)
+    lens, S, out_len, K = [7, 4], 7, 5, 3
+    ids = g.integers(0, cfg.vocab_size - 1, size=(2, S)).astype(np.int32)
+    ids[1, 4:] = cfg.end_id
+    res = ref.forward_beam(ids, lens, out_len, K)
+    out, sl, cum = res["output_ids"], res["sequence_lengths"], res["cum_log_probs"]
+    assert out.shape == (2, K, S + out_len) and sl.shape == (2, K) and cum.shape == (2, K)
+    for b in range(2):
+        for j in range(K):
+            assert np.array_equal(out[b, j, :lens[b]], ids[b, :lens[b]])
+            n_gen = int(sl[b, j]) - S
+            assert 1 <= n_gen <= out_len
+            assert (out[b, j, lens[b] + n_gen:] == cfg.end_id).all()
+        assert (np.diff(cum[b]) <= 0).all()
+    again = ref.forward_beam(ids, lens, out_len, K, decide_on_logits=np.stack(res["logits"]))
+    assert np.array_equal(again["output_ids"], out) and np.array_equal(again["sequence_lengths"], sl)
